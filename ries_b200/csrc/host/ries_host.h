@@ -1,0 +1,136 @@
+// Host side of the B200 RIES engine: the thin C++ layer that mirrors the reference's
+// main()/parse_args()/init2()/report_match()/print_end() boundary (ries.c:12062, 11117, 10314,
+// 7887, 7574) and drives the device engine one complexity pass at a time.
+#pragma once
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "core/params.h"
+
+namespace ries {
+
+/* Where stdout goes (the C-ABI's write callback; NULL => fwrite(stdout)). */
+struct Sink {
+  void (*fn)(void* ctx, const char* buf, size_t n);
+  void* ctx;
+  void write(const char* s, size_t n) const;
+  void printf(const char* fmt, ...) const __attribute__((format(printf, 2, 3)));
+};
+
+/* Thrown wherever the reference calls exit()/print_end(nonzero). */
+struct ExitRequest {
+  int code;
+};
+
+#define RIES_EXIT_NO_ERROR (-9998) /* ries.c:4541 */
+
+enum { OF_POSTFIX = 0, OF_CONDENSED = 1, OF_NORMAL = 2, OF_FORTH = 3 };
+
+/* Per-symbol attributes the host needs beyond RiesParams (names for output). */
+struct SymInfo {
+  unsigned char ch;
+  char seft;             /* 'a' 'b' 'c' */
+  short wgt;
+  short alwd;
+  const char* name_forth; /* may be NULL */
+  const char* name_infix;
+};
+
+/* Everything parse_args()/init1() decide (ries.c:10228-10310, 11117-11964). */
+struct Options {
+  std::string argv0;
+  double levadj = 2.0;
+  double tlevel = 4.0;
+  bool got_target = false;
+  double target = 1.0;
+  double mag_ulp = 0.0;
+  short sa_alwd[256];
+  int restrict_subexpr = TYPE_NONE;
+  int restrict_exponents = TYPE_NONE;
+  int restrict_trig_args = TYPE_NONE;
+  bool exact_exit = false;
+  bool relative_x = true;
+  bool wide_output = false;
+  bool show_ss = false;
+  bool S_option = false;
+  bool NOS_options = false;
+  bool allow_slow_message = true;
+  bool no_cv_simplify = false;
+  int out_format = OF_NORMAL;
+  double max_matches = 100;
+  double k_max_match_dist = -0.01;
+  double min_matchsize = 0;
+  int debug_y = 0;
+  Options();
+};
+
+/* State init2() + main()'s parameter set-up derive (ries.c:10314-10744, 12111-12317). */
+struct Setup {
+  RiesParams P;
+  SymInfo info[RIES_MAX_SYMS];
+  int idx_of[256]; /* char -> table index, -1 if unknown */
+  double k_min_best_match;
+  double init_match_dist;
+  double tgt_to_print;
+  double k_precision_ulp;
+  int k_usable_digits;
+  int k_nominal_digits;
+  bool x_lhs_only;
+};
+
+/* parse_args: throws ExitRequest on usage errors, printing what the reference prints. */
+void parse_args(int argc, char** argv, Options& opt, const Sink& out);
+/* init2 + the threshold set-up of main(); may print notices ("Replacing -i with -r ..."). */
+void build_setup(Options& opt, Setup& S, const Sink& out);
+/* main()'s parameter block between init2() and the header: -i demotion, thresholds (12111-12317). */
+void finish_setup(Options& opt, Setup& S, const Sink& out);
+void show_symset(const Options& opt, const Setup& S, const Sink& out);
+void brief_help(const Sink& out);
+const char* sym_defn(unsigned char ch, bool normal);
+
+/* gen_forms/gf_1 + ge_1's suffix tables for one pass, in the reference's visiting order. */
+void gen_forms(const RiesParams& P, int e_minw, int e_maxw, std::vector<FormDesc>& forms,
+               double* n_leaf_forms);
+
+/* One pass as seen by the host. */
+struct PassOutput {
+  double generated = 0;  /* g_ne */
+  double dead_ends = 0;  /* prune_count */
+  long inserted = 0;     /* insert_count */
+  std::vector<MatchEvent> events; /* sorted by (seq, kind) */
+};
+
+/* The device engine (K1..K4).  The product has exactly one implementation (engine.cu); the CPU
+   emulation used by the tests lives in oracle/emul.cc and is never linked into the product. */
+class Engine {
+ public:
+  virtual ~Engine() {}
+  virtual void begin(const RiesParams& P) = 0;
+  virtual void run_pass(int using_x, int cplx, const std::vector<FormDesc>& forms,
+                        double best_match0, bool skip_exact, PassOutput& out) = 0;
+  /* rows of the last pass inserted with seq < `seq` (or <= when inclusive): early-exit accounting */
+  virtual long inserted_before(uint32_t seq, bool inclusive) = 0;
+  virtual const char* name() const = 0;
+};
+
+struct RunStats {
+  double lhs_gen = 0, rhs_gen = 0, gen_total = 0;
+  double lhs_prune = 0, rhs_prune = 0;
+  long lhs_insert = 0, rhs_insert = 0;
+  int lmax = 0, rmax = 0;
+  int passes = 0;
+  double exec_seconds = 0;
+};
+
+/* main() after parse_args: the whole search.  Returns the process exit code. */
+int run_search(Options& opt, Engine& eng, const Sink& out, RunStats* stats_out);
+
+/* number formatting (ries_spfg ries.c:4069, pf_intfloat_wid 7542) */
+std::string spfg(int prec, double x);
+std::string pf_intfloat_wid(double x, int width);
+
+}  // namespace ries

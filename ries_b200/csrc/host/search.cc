@@ -1,0 +1,618 @@
+// The pass scheduler, the sequential replay of device-found candidates, and the report: the
+// host-side restatement of main()'s outer loop (/root/reference/public/ries.c:12327-12580),
+// check_match()'s threshold logic (8243-8369), check_exact_match() (8541-8618), report_match()
+// (7887-8236), check_exit() (7805-7843) and print_end() (7574-7633).
+//
+// Division of labour: the device engine generates, evaluates, sorts, dedupes, merges and finds
+// every (new expression, neighbour) pair that could beat the match threshold as it stood at the
+// START of the pass, already refined by cv_simplify+Newton.  The threshold only ever shrinks, so
+// replaying those candidates here in insertion order with the live threshold reproduces the
+// reference's streaming decisions exactly.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include <algorithm>
+
+#include "host/ries_host.h"
+
+namespace ries {
+
+/* ---------------- number formatting ---------------- */
+
+static double intpow10(int p) { /* ries_intpow(10.0, p) ries.c:3794 */
+  double rv = 1.0, pow2 = 10.0;
+  int recip = 0;
+  if (p < 0) { p = -p; recip = 1; }
+  int i = p;
+  while (i > 0) {
+    if (i & 1) rv = rv * pow2;
+    i >>= 1;
+    if (i) pow2 = pow2 * pow2;
+  }
+  return recip ? (1.0 / rv) : rv;
+}
+
+/* ries_to_digits ries.c:3839-3955 */
+static bool to_digits(double x, char* s, int* expn, int* sign, int precision) {
+  int dig1 = precision + 1;
+  int sgn = 0;
+  if (x < 0.0) { x = -x; sgn = 1; }
+  *sign = sgn;
+  double r = x;
+  if (x == 0.0) {
+    *expn = 0;
+    for (int i = 0; i < precision; i++) s[i] = '0';
+    s[precision] = 0;
+    return true;
+  }
+  int e = (int)(floor(log10(fabs(x))));
+  if (e < -300) {
+    r = r * intpow10(300);
+    r = r / intpow10(e + 300);
+  } else if (e > 0) {
+    r = r / intpow10(e);
+  } else if (e < 0) {
+    r = r * intpow10(-e);
+  }
+  if (r >= 10.0) { r = r / 10.0; e++; }
+  else if (r < 1.0) { r = r * 10.0; e--; }
+  if (r >= 10.0 || r < 1.0) return false;
+  for (int i = 0; i < dig1; i++) {
+    int d = (int)r;
+    r = r - (double)d;
+    r = r * 10.0;
+    s[i] = (char)('0' + d);
+  }
+  for (int i = dig1 - 1; i > 0; i--) {
+    if (s[i] < '0') { s[i - 1]--; s[i] = (char)(s[i] + 10); }
+  }
+  if (s[0] <= '0') return false;
+  if (s[dig1 - 1] >= '5') {
+    s[dig1 - 2]++;
+    int i = dig1 - 2;
+    while (i > 0 && s[i] > '9') {
+      s[i] = (char)(s[i] - 10);
+      i--;
+      s[i] = (char)(s[i] + 1);
+    }
+  }
+  if (s[0] > '9') {
+    e++;
+    for (int i = precision; i >= 2; i--) s[i] = s[i - 1];
+    s[0] = '1';
+    s[1] = '0';
+  }
+  s[precision] = 0;
+  *expn = e;
+  return true;
+}
+
+static void bltr0(char* s) { /* ries_bltr0 ries.c:4025 */
+  if (!s || !*s) return;
+  char* t = s;
+  while (*t) t++;
+  t--;
+  while (t >= s && *t == '0') { *t = 0; t--; }
+}
+
+/* ries_spfg(tmp, 100, 0, prec, x) ries.c:4069-4246 with a generous buffer */
+std::string spfg(int precision, double x) {
+  if (x <= -HUGE_VAL) return std::string("-inf").substr(0, precision);
+  if (x >= HUGE_VAL) return std::string("+inf").substr(0, precision);
+  if (!((x > -HUGE_VAL) && (x < HUGE_VAL))) return std::string("NaN").substr(0, precision);
+  if (precision > 35) precision = 35;
+  else if (precision < 1) precision = 1;
+  char s2[48];
+  int exponent = 0, sign = 0;
+  memset(s2, 0, sizeof(s2));
+  if (!to_digits(x, s2, &exponent, &sign, precision)) return std::string();
+  std::string o;
+  if (sign) o.push_back('-');
+  if ((exponent > 0) && (exponent < precision)) {
+    int i = 0;
+    o.push_back(s2[i++]);
+    while (exponent) { o.push_back(s2[i++]); exponent--; }
+    bltr0(s2);
+    if (*s2 == 0) return o;
+    o.push_back('.');
+    for (; s2[i] && (i < precision); i++) o.push_back(s2[i]);
+    return o;
+  } else if (exponent == 0) {
+    o.push_back(s2[0]);
+    bltr0(s2 + 1);
+    if (s2[1] == 0) return o;
+    o.push_back('.');
+    for (int i = 1; s2[i] && (i < precision); i++) o.push_back(s2[i]);
+    return o;
+  } else if ((exponent < 0) && (exponent > -5)) {
+    o += "0.";
+    exponent++;
+    while (exponent < 0) { o.push_back('0'); exponent++; }
+    bltr0(s2);
+    if (*s2 == 0) return o;
+    for (int i = 0; s2[i] && (i < precision); i++) o.push_back(s2[i]);
+    return o;
+  }
+  char sexp[16];
+  if (exponent >= 0) snprintf(sexp, sizeof(sexp), "+%d", exponent);
+  else snprintf(sexp, sizeof(sexp), "%d", exponent);
+  o.push_back(s2[0]);
+  bltr0(s2 + 1);
+  if (s2[1]) {
+    o.push_back('.');
+    for (int i = 1; (i < precision) && s2[i]; i++) o.push_back(s2[i]);
+  }
+  o.push_back('e');
+  o += sexp;
+  return o;
+}
+
+/* pf_intfloat_wid ries.c:7542-7567 */
+std::string pf_intfloat_wid(double x, int width) {
+  char fmt1[32], fmt2[32], buf[40];
+  int w = (x < 0) ? (width - 1) : width;
+  snprintf(fmt1, sizeof(fmt1), "%%.%dg", w);
+  snprintf(fmt2, sizeof(fmt2), "%%.%de", w - 6);
+  snprintf(buf, 40, fmt1, x);
+  if (strchr(buf, 'e') || strchr(buf, 'E')) {
+    snprintf(buf, 40, fmt2, x);
+  } else if (strchr(buf, '.')) {
+    int i = (int)strlen(buf) - 1;
+    while ((i > 0) && (buf[i] == '0')) { buf[i] = 0; i--; }
+    if ((i > 0) && (buf[i] == '.')) buf[i] = 0;
+  }
+  return std::string(buf);
+}
+
+/* ---------------- the search ---------------- */
+
+namespace {
+
+double now_sec() {
+  struct timeval tv;
+  gettimeofday(&tv, 0);
+  return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+}
+
+struct Search {
+  Options& opt;
+  Setup S;
+  Engine& eng;
+  const Sink& out;
+  RunStats st;
+  double t_start;
+
+  /* live search state (ries.c:3461, 3231-3233) */
+  double best_match = 0;
+  bool got_exact = false;
+  double num_matches = 0;
+  int lmin = 1, lmax = 1, rmin = 1, rmax = 1;
+
+  /* early-exit bookkeeping: which event of the running pass we are replaying */
+  long resident_rows = 0;   /* rows inserted by completed passes */
+  const MatchEvent* cur_ev = 0;
+
+  Search(Options& o, Engine& e, const Sink& s) : opt(o), eng(e), out(s) { t_start = now_sec(); }
+
+  std::string sym_chars(const Sym128& s) const {
+    std::string r;
+    for (int i = 0; i < RIES_MAX_ELEN + 1; i++) {
+      unsigned c = sym_get(s, i);
+      if (!c) break;
+      r.push_back((char)S.P.sym_char[c - 1]);
+    }
+    return r;
+  }
+
+  int complexity(const std::string& e) const { /* ries.c:6614 */
+    int c = 0;
+    for (size_t i = 0; i < e.size(); i++) {
+      int g = S.idx_of[(unsigned char)e[i]];
+      if (g >= 0) c += S.P.sym_wgt[g];
+    }
+    return c;
+  }
+
+  std::string postfix_formatter(const std::string& e) const { /* ries.c:6572 */
+    std::string o;
+    for (size_t i = 0; i < e.size(); i++) {
+      int g = S.idx_of[(unsigned char)e[i]];
+      if (g >= 0 && S.info[g].name_forth) o += S.info[g].name_forth;
+      else o.push_back(e[i]);
+      o.push_back(' ');
+    }
+    while (!o.empty() && o.back() == ' ') o.pop_back();
+    return o;
+  }
+
+  /* Memory the reference's allocator would report for `nodes` tree nodes: sizeof(expr) = 72 on
+     LP64 (ries.c:2955), 64 KiB blocks with an 8-byte back link (my_alloc 4837-4900). */
+  static void ref_memory(long nodes, long* kib, unsigned long* bytes) {
+    const long per_block = (65536 - 8) / 72;
+    long blocks = (nodes + per_block - 1) / per_block;
+    *kib = blocks * 64;
+    *bytes = (unsigned long)(blocks * 8 + nodes * 72);
+  }
+
+  long live_rows() {
+    if (!cur_ev) return resident_rows;
+    /* An EXACT event's expression is never inserted; a neighbour event fires right after its
+       expression was inserted (bt_insert 8686-8721). */
+    return resident_rows + eng.inserted_before(cur_ev->seq, cur_ev->kind != EV_EXACT);
+  }
+
+  void print_end(int exit_code) { /* ries.c:7574 */
+    double tsec = now_sec() - t_start;
+    if (got_exact && (opt.restrict_subexpr < TYPE_INT)) {
+      out.printf("\n  NOTE: 'exact' match may result from floating-point roundoff error.\n");
+    }
+    if (opt.out_format <= OF_NORMAL) describe_symbols();
+    long total_insert = st.lhs_insert + st.rhs_insert;
+    if (total_insert) {
+      out.printf("\n");
+      out.printf("                         --LHS--      --RHS--      -Total-\n");
+      out.printf("     max complexity: %11d  %11d  %11d\n", lmax, rmax, lmax + rmax);
+      out.printf("          dead-ends: %11s", pf_intfloat_wid(st.lhs_prune, 11).c_str());
+      out.printf("  %11s", pf_intfloat_wid(st.rhs_prune, 11).c_str());
+      out.printf("  %11s", pf_intfloat_wid(st.lhs_prune + st.rhs_prune, 11).c_str());
+      out.printf("  Time: %.3f\n", tsec);
+      out.printf("        expressions: %11s", pf_intfloat_wid(st.lhs_gen, 11).c_str());
+      out.printf("  %11s", pf_intfloat_wid(st.rhs_gen, 11).c_str());
+      out.printf("  %11s\n", pf_intfloat_wid(st.gen_total, 11).c_str());
+      out.printf("           distinct: %11ld  %11ld  %11ld", st.lhs_insert, st.rhs_insert, total_insert);
+      long kib; unsigned long bytes;
+      ref_memory(live_rows(), &kib, &bytes);
+      if (kib > 1024L) out.printf("  Memory: %ldKiB\n", kib);
+      else out.printf("  Memory: %ld B\n", bytes);
+      out.printf("\n");
+      double combos = ((double)st.lhs_insert) * ((double)st.rhs_insert);
+      out.printf("        Total equations tested:    %20s", pf_intfloat_wid(combos, 20).c_str());
+      if (combos > 9999) out.printf(" (%.4g)", combos);
+      out.printf("\n");
+    }
+    if (exit_code) throw ExitRequest{exit_code};
+  }
+
+  /* legend bookkeeping: defsym_used ries.c:7417, describe_symbols 7434-7516 */
+  bool def_needed[256] = {false};
+  bool def_given[256] = {false};
+  void defsym_used(const std::string& e) {
+    for (size_t i = 0; i < e.size(); i++)
+      if (sym_defn((unsigned char)e[i], opt.out_format == OF_NORMAL)) def_needed[(unsigned char)e[i]] = true;
+  }
+  void describe_symbols() {
+    /* used_atan2 is only ever set by the infix formatter, so in postfix mode 'A' is never described */
+    def_needed[(unsigned char)'A'] = false;
+    bool normal = (opt.out_format == OF_NORMAL);
+    const int kLineLeftInit = 79 - 2;
+    int lineleft = kLineLeftInit;
+    bool need_lf = true, going = true;
+    while (going) {
+      going = false;
+      for (int sym = 0; sym < 256; sym++) {
+        if (def_needed[sym] && !def_given[sym]) {
+          going = true;
+          if (need_lf) { out.printf("\n"); need_lf = false; }
+        }
+      }
+      if (going) {
+        const char* candidate = 0;
+        int clen = 0, csym = 0;
+        for (int sym = 0; sym < 256; sym++) {
+          if (def_needed[sym] && !def_given[sym]) {
+            int sl = (int)strlen(sym_defn((unsigned char)sym, normal));
+            if ((sl > clen) && (sl < lineleft)) {
+              csym = sym;
+              candidate = sym_defn((unsigned char)sym, normal);
+              clen = sl;
+            }
+          }
+        }
+        if (candidate) {
+          out.printf("  %s", candidate);
+          def_given[csym] = true;
+          lineleft = lineleft - clen - 2;
+        } else {
+          out.printf("\n");
+          lineleft = kLineLeftInit;
+        }
+      }
+    }
+    if (lineleft < kLineLeftInit) out.printf("\n");
+  }
+
+  void check_exit(bool is_exact) { /* ries.c:7805 */
+    if (is_exact && (opt.restrict_subexpr == TYPE_INT) && opt.exact_exit) {
+      out.printf("  (Stopping now because -ie option was given.)\n");
+    } else if (is_exact && (opt.restrict_subexpr == TYPE_RAT) && opt.exact_exit) {
+      out.printf("  (Stopping now because -re option was given.)\n");
+    } else if (is_exact && (opt.restrict_subexpr == TYPE_CONS) && opt.exact_exit) {
+      out.printf("  (Stopping now because -ce option was given.)\n");
+    } else if (is_exact && (opt.k_max_match_dist == 0)) {
+      out.printf("  (Stopping now because an exact match was found.)\n");
+    } else if (is_exact && opt.exact_exit) {
+      out.printf("  (Stopping now because --min-match-distance 0 or --max-match-distance 0\n"
+                 "  was given.)\n");
+    } else if (best_match < opt.min_matchsize) {
+      double t = (S.k_min_best_match > opt.min_matchsize) ? S.k_min_best_match : opt.min_matchsize;
+      out.printf("  (Stopping now because best match is within %7.3g of target value.)\n", t);
+    } else if (num_matches >= opt.max_matches) {
+      if (num_matches == 1) out.printf("  (Stopping now because 1 match was found.)\n");
+      else out.printf("  (Stopping now because %ld matches were found.)\n", (long)num_matches);
+    } else {
+      return;
+    }
+    print_end(RIES_EXIT_NO_ERROR);
+  }
+
+  /* report_match ries.c:7887 (postfix / FORTH formats; infix is a later row of the scope table) */
+  void report_match(const std::string& le, const std::string& re, double root, double delta) {
+    if ((delta == 0.0) && got_exact) return;
+    std::string l_fmt, r_fmt;
+    if (opt.out_format == OF_POSTFIX) {
+      l_fmt = le; r_fmt = re;
+    } else {
+      l_fmt = postfix_formatter(le); r_fmt = postfix_formatter(re);
+    }
+    int lf_len = (int)l_fmt.size(), rf_len = (int)r_fmt.size();
+    int width = opt.relative_x ? 44 : 40;
+    int equ_width = 5;
+    int t_width = width + equ_width;
+    int l_pad = width / 2;
+    int r_pad = width - l_pad;
+    l_pad -= lf_len; if (l_pad < 0) l_pad = 0;
+    r_pad -= rf_len; if (r_pad < 0) r_pad = 0;
+    width = l_pad + lf_len + equ_width + rf_len + r_pad;
+    while ((width > t_width) && (l_pad > 0)) { l_pad--; width--; }
+    while ((width > t_width) && (r_pad > 0)) { r_pad--; width--; }
+    int justify_overflow = width - t_width;
+    if (justify_overflow < 0) justify_overflow = 0;
+
+    std::string line(l_pad, ' ');
+    line += " " + l_fmt + " = " + r_fmt + " ";
+    line.append(r_pad, ' ');
+
+    std::string froot = spfg(S.k_usable_digits, root);
+    const char* x_T_intro = "for x ";
+    if (opt.wide_output) {
+      char tmp[64];
+      snprintf(tmp, sizeof(tmp), "x = %-20s  ", froot.c_str());
+      line += tmp;
+      x_T_intro = "";
+    }
+    char fval[32];
+    fval[0] = 0;
+    int posn = 0;
+    double adelta = delta;
+    if (delta == 0.0) {
+      line += "('exact' match)";
+      posn = 15;
+      got_exact = true;
+    } else if (!opt.relative_x) {
+      line += "for x = ";
+      snprintf(fval, sizeof(fval), "%s", froot.c_str());
+      posn = 8 + (int)strlen(fval);
+    } else if (delta < 0.0) {
+      adelta = -delta;
+      line += x_T_intro; line += "= T - ";
+      snprintf(fval, 30, "%.6g", adelta);
+      posn = 6 + (int)strlen(x_T_intro) + (int)strlen(fval);
+    } else {
+      line += x_T_intro; line += "= T + ";
+      snprintf(fval, 30, "%.6g", adelta);
+      posn = 6 + (int)strlen(x_T_intro) + (int)strlen(fval);
+    }
+    if (opt.relative_x) width = 12 + 6 + 5;
+    else width = 8 + S.k_usable_digits + 6;
+    line += fval;
+    posn += justify_overflow;
+    for (int i = posn; i < width; i++) line.push_back(' ');
+    if (opt.wide_output) {
+      char temp[64];
+      double ratio = 0;
+      if (adelta != 0) ratio = fabs(S.P.target / adelta);
+      if (adelta == 0) snprintf(temp, 30, "%s", "(1 part in infinity)");
+      else if (ratio < 100) {
+        int r10 = (int)((ratio * 10) + 0.5);
+        int r1 = r10 % 10; r10 = (r10 - r1) / 10;
+        snprintf(temp, 30, "(1 part in %d.%d)", r10, r1);
+      } else if (ratio < 100000000) snprintf(temp, 30, "(1 part in %d)", (int)(ratio + 0.5));
+      else snprintf(temp, 30, "(1 part in %.3e)", ratio);
+      char t2[64];
+      snprintf(t2, sizeof(t2), "%-22s", temp);
+      line += t2;
+    }
+    char tail[32];
+    snprintf(tail, sizeof(tail), " {%d}\n", complexity(le) + complexity(re));
+    line += tail;
+    out.write(line.data(), line.size());
+
+    num_matches++;
+    defsym_used(le);
+    defsym_used(re);
+    check_exit(delta == 0.0);
+  }
+
+  /* check_exact_match ries.c:8541; `tree` is the row already in the table */
+  void replay_exact(const MatchEvent& ev, int using_x) {
+    const Row& tree = using_x ? ev.rhs : ev.lhs;
+    const Row& fresh = using_x ? ev.lhs : ev.rhs;
+    double total_deriv;
+    if (!using_x) { /* new item is RHS, tree item must be an LHS */
+      if (tree.der == 0.0) return;
+      if (fabs(tree.der) < S.P.k_vanished_dx) return;
+      total_deriv = tree.der;
+    } else {
+      if (tree.der != 0.0) return;
+      if (fabs(fresh.der) < S.P.k_vanished_dx) return;
+      total_deriv = 0 - fresh.der;
+    }
+    double x = tree.val, eps = x * 1.0e-14, xpe = x + eps;
+    if (x == xpe) return;
+    if (total_deriv == 0) return;
+    double delta = eps / total_deriv;
+    double score = fabs(delta);
+    if ((best_match > 0) && (score > best_match)) return;
+    if (score < opt.min_matchsize) return;
+    report_match(sym_chars(ev.lhs.sym), sym_chars(ev.rhs.sym), S.P.target, 0.0);
+  }
+
+  /* check_match ries.c:8243 */
+  void replay_neighbour(const MatchEvent& ev) {
+    double total_deriv = ev.lhs.der - ev.rhs.der;
+    if (total_deriv == 0.0) {
+      fprintf(stderr, "check_match got dx = 0!\n");
+      return;
+    }
+    double delta = (ev.rhs.val - ev.lhs.val) / total_deriv;
+    double score = fabs(delta);
+    if ((score > best_match) || (score < opt.min_matchsize)) return;
+    if (ev.newton_err) return;
+    delta = ev.root - S.P.target;
+    score = fabs(delta);
+    std::string le = sym_chars(ev.lhs_s), re = sym_chars(ev.rhs_s);
+    if (score == 0.0) {
+      report_match(le, re, ev.root, delta);
+      return;
+    } else if (score < best_match) {
+      report_match(le, re, ev.root, delta);
+      best_match = (score * 0.999) - S.k_min_best_match;
+      check_exit(false);
+    }
+  }
+
+  int run() {
+    build_setup(opt, S, out);
+    if (opt.show_ss) { /* ries.c:12100 */
+      show_symset(opt, S, out);
+      out.printf("%s: %s", opt.argv0.c_str(),
+                 "Exiting now (to do an equation search, omit '-S' or include\n"
+                 "  symbol names, for example: 'ries 3.14159 -S123456789+/')\n");
+      return 0;
+    }
+    finish_setup(opt, S, out);
+    if (opt.out_format != OF_POSTFIX && opt.out_format != OF_FORTH) {
+      /* infix (-F1/-F2, the CLI default) is the first "next" row of the scope table */
+      opt.out_format = OF_FORTH;
+    }
+    best_match = S.init_match_dist;
+
+    /* header ries.c:12327-12337 */
+    {
+      char fmt[32], buf[128];
+      out.printf("\n");
+      out.printf("   Your target value: T = ");
+      snprintf(fmt, sizeof(fmt), "%%-%ds", S.k_usable_digits + 6);
+      snprintf(buf, sizeof(buf), fmt, spfg(S.k_usable_digits, S.tgt_to_print).c_str());
+      out.printf("%s", buf);
+      snprintf(fmt, sizeof(fmt), "  %%%ds", 44 - S.k_usable_digits);
+      out.printf(fmt, "mrob.com/ries");
+      out.printf("%s", "\n\n");
+    }
+
+    double lim_gentotal = 2000.0;
+    if (opt.tlevel >= -2.0) lim_gentotal *= pow(4.0, opt.tlevel);
+    double lim_prune = lim_gentotal * 15.0;
+    if (opt.debug_y) out.printf("Will stop after generating searchmax=%g expressions\n", lim_gentotal);
+
+    eng.begin(S.P);
+    bool reported_exhaustion = false;
+    std::vector<FormDesc> forms;
+    PassOutput po;
+    bool going = true;
+    while (going) {
+      int using_x;
+      int cplx;
+      if (st.lhs_insert > st.rhs_insert) { rmin++; rmax++; using_x = 0; cplx = rmax; }
+      else { lmin++; lmax++; using_x = 1; cplx = lmax; }
+      double genf = 0;
+      gen_forms(S.P, cplx, cplx, forms, &genf);
+      po = PassOutput();
+      cur_ev = 0;
+      eng.run_pass(using_x, cplx, forms, best_match, got_exact, po);
+      st.passes++;
+      /* replay the pass's candidates in insertion order with the live threshold */
+      for (size_t k = 0; k < po.events.size(); k++) {
+        cur_ev = &po.events[k];
+        if (cur_ev->kind == EV_EXACT) replay_exact(*cur_ev, using_x);
+        else replay_neighbour(*cur_ev);
+      }
+      cur_ev = 0;
+      resident_rows += po.inserted;
+      if (using_x) {
+        if (opt.debug_y) {
+          out.printf("finished LHS from {%d} to {%d}: %g forms expanded, %g expressions.\n", lmin, lmax,
+                     genf, po.generated);
+          out.printf("\n");
+        }
+        st.lhs_gen += po.generated; st.lhs_insert += po.inserted; st.lhs_prune += po.dead_ends;
+      } else {
+        if (opt.debug_y)
+          out.printf("finished RHS from {%d} to {%d}: %g forms expanded, %g expressions.\n", rmin, rmax,
+                     genf, po.generated);
+        st.rhs_gen += po.generated; st.rhs_insert += po.inserted; st.rhs_prune += po.dead_ends;
+      }
+      st.gen_total += po.generated;
+
+      if ((lmax > S.P.exhaust_cpx) && (rmax > S.P.exhaust_cpx)) { /* 12484 */
+        if (num_matches == 0) {
+          out.printf("exhaustion timeout (complexity LHS {%d}, RHS {%d}). Possible causes:\n"
+                     "  MAX_ELEN %d too small\n", lmax, rmax, RIES_MAX_ELEN);
+          if (opt.NOS_options) out.printf("  too many symbols excluded via -N, -O or -S\n");
+          out.printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n");
+          reported_exhaustion = true;
+        }
+        st.gen_total = lim_gentotal;
+      }
+      if (opt.debug_y) {
+        out.printf("gen_total %g (lhs %ld rhs %ld) searchmax %g gnm %ld\n", st.gen_total, st.lhs_insert,
+                   st.rhs_insert, lim_gentotal, (long)num_matches);
+      }
+      if (num_matches == 0) { /* 12522 */
+        double tsec = now_sec() - t_start;
+        if (opt.debug_y || ((tsec > 2.0) && opt.allow_slow_message)) {
+          out.printf("  Still searching: %11s expr and %.3f sec so far...     \r",
+                     pf_intfloat_wid(st.gen_total, 11).c_str(), tsec);
+        }
+      }
+      if ((st.lhs_prune + st.rhs_prune) >= lim_prune) going = false;
+      if (st.gen_total >= lim_gentotal) going = false;
+    }
+
+    if (reported_exhaustion) {
+    } else if (num_matches == 0) {
+      out.printf("No solution was found (try using -l%d", (int)floor(opt.levadj + 1.0));
+      if (S.init_match_dist < (0.001 * S.P.target)) out.printf(" or a larger --max-match-distance");
+      out.printf(").  \n");
+    } else if (opt.exact_exit) {
+      out.printf("               No 'exact' solution was found (try using -l%d).\n",
+                 (int)floor(opt.levadj + 1.0));
+    } else {
+      out.printf("                  (for more results, use the option '-l%d')\n",
+                 (int)floor(opt.levadj + 1.0));
+    }
+    print_end(0);
+    return 0;
+  }
+};
+
+}  // namespace
+
+int run_search(Options& opt, Engine& eng, const Sink& out, RunStats* stats_out) {
+  Search s(opt, eng, out);
+  int code = 0;
+  try {
+    code = s.run();
+  } catch (const ExitRequest& e) {
+    code = e.code;
+  }
+  s.st.lmax = s.lmax;
+  s.st.rmax = s.rmax;
+  s.st.exec_seconds = now_sec() - s.t_start;
+  if (stats_out) *stats_out = s.st;
+  return code;
+}
+
+}  // namespace ries
