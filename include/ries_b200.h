@@ -1,0 +1,49 @@
+/* ries_b200 -- C ABI of the B200-native RIES search engine (libries_b200.so).
+ *
+ * This is the boundary a maintainer of thomasahle/ries binds instead of the emscripten module: the
+ * web worker calls `moduleInstance.callMain([...args, target])` and collects what the program prints
+ * (src/workers/ries.worker.js:100-113, 226-234); natively that is ries.c's
+ * `int main(int nargs, char *argv[])` (public/ries.c:12062) writing to stdout.  Plain pointers and
+ * sizes only; no C++ or torch types cross this line.  INTEGRATION.md shows the N-API / ctypes stubs.
+ */
+#ifndef RIES_B200_H
+#define RIES_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Receives program output in order (the replacement for Module.print / stdout). */
+typedef void (*ries_write_fn)(void *ctx, const char *buf, size_t n);
+
+/* Replaces main(argc, argv) of public/ries.c:12062 (wasm export `_main` / `callMain`).
+ * argv[0] is the program name, the target number and options follow exactly as for `ries`.
+ * Output that the reference prints to stdout goes to `out` (NULL => the process's stdout).
+ * Returns the status the reference would have passed to exit(): 0 normal end, -9998 for every
+ * "(Stopping now because ...)" early stop (ries.c:4541, seen by a shell as 242), -1 usage error,
+ * 1 missing target.  3 = no CUDA device (this library has no CPU search path).
+ * Not re-entrant (one search at a time per process, like the reference's global state,
+ * ries.c:3201-3538); the device is chosen with the RIES_DEVICE environment variable. */
+int ries_main(int argc, char **argv, ries_write_fn out, void *ctx);
+
+/* Counters of the most recent ries_main() call (the stats block of print_end, ries.c:7599-7628,
+ * as numbers) -- what bench.py divides by time. */
+typedef struct ries_run_stats {
+  double lhs_expressions, rhs_expressions; /* lhs_gen, rhs_gen */
+  double lhs_dead_ends, rhs_dead_ends;     /* lhs_prune, rhs_prune */
+  long long lhs_distinct, rhs_distinct;    /* lhs_insert, rhs_insert */
+  int lhs_max_complexity, rhs_max_complexity;
+  int passes;
+  int exit_code;
+  double seconds;                           /* wall time inside ries_main */
+  unsigned long long kernel_launches;      /* CUDA kernels this call launched */
+} ries_run_stats;
+void ries_last_stats(ries_run_stats *out);
+
+/* "sm_100a" when the CUDA engine is usable in this process, else a diagnostic string. */
+const char *ries_engine_name(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

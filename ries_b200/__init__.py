@@ -1,0 +1,11 @@
+"""ries_b200 -- B200-native RIES search engine behind the reference's own boundary.
+
+The reference (thomasahle/ries) reaches its engine as ``callMain([...flags, target])`` on the wasm
+build of ``public/ries.c`` and parses what it prints (src/workers/ries.worker.js:226-234).  This package
+is the same call over the C ABI of ``libries_b200.so`` (include/ries_b200.h): every search stage runs in
+hand-written sm_100a CUDA kernels; there is no CPU search path and importing the engine fails loudly if
+the shared library is missing.
+"""
+from .api import RiesError, call_main, engine_name, last_stats, lib_path, run  # noqa: F401
+
+__all__ = ["call_main", "run", "last_stats", "engine_name", "lib_path", "RiesError"]

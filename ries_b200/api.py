@@ -1,0 +1,79 @@
+"""ctypes binding of include/ries_b200.h (the same stub INTEGRATION.md shows for other hosts)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libries_b200.so")
+_lib = None
+
+_WRITE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_char), ctypes.c_size_t)
+
+
+class RiesError(RuntimeError):
+    pass
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [
+        ("lhs_expressions", ctypes.c_double), ("rhs_expressions", ctypes.c_double),
+        ("lhs_dead_ends", ctypes.c_double), ("rhs_dead_ends", ctypes.c_double),
+        ("lhs_distinct", ctypes.c_longlong), ("rhs_distinct", ctypes.c_longlong),
+        ("lhs_max_complexity", ctypes.c_int), ("rhs_max_complexity", ctypes.c_int),
+        ("passes", ctypes.c_int), ("exit_code", ctypes.c_int),
+        ("seconds", ctypes.c_double), ("kernel_launches", ctypes.c_ulonglong),
+    ]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RiesError(
+                "ries_b200: %s is missing -- build it with `python -m ries_b200.build` "
+                "(there is no CPU fallback)" % _LIB_PATH)
+        lib = ctypes.CDLL(_LIB_PATH)
+        lib.ries_main.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), _WRITE_FN, ctypes.c_void_p]
+        lib.ries_main.restype = ctypes.c_int
+        lib.ries_last_stats.argtypes = [ctypes.POINTER(_Stats)]
+        lib.ries_last_stats.restype = None
+        lib.ries_engine_name.argtypes = []
+        lib.ries_engine_name.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def call_main(args, prog="ries"):
+    """``callMain(args)`` of the wasm module: returns (exit_code, everything printed)."""
+    lib = _load()
+    argv = [prog.encode()] + [a.encode() if isinstance(a, str) else a for a in args]
+    arr = (ctypes.c_char_p * (len(argv) + 1))(*argv, None)
+    chunks = []
+
+    def _write(_ctx, buf, n):
+        chunks.append(ctypes.string_at(buf, n))
+
+    cb = _WRITE_FN(_write)
+    code = lib.ries_main(len(argv), arr, cb, None)
+    return code, b"".join(chunks).decode("utf-8", "replace")
+
+
+def run(target, *flags):
+    """Convenience: ``run("2.5063", "-l4", "-F3")`` -> printed report (raises on usage errors)."""
+    code, text = call_main(list(flags) + [str(target)])
+    if code not in (0, -9998):
+        raise RiesError("ries exited with status %d:\n%s" % (code, text))
+    return text
+
+
+def last_stats():
+    s = _Stats()
+    _load().ries_last_stats(ctypes.byref(s))
+    return {name: getattr(s, name) for name, _ in _Stats._fields_}
+
+
+def engine_name():
+    return _load().ries_engine_name().decode()

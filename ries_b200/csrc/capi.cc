@@ -1,0 +1,58 @@
+// C ABI (include/ries_b200.h): main(argc, argv) of the reference (ries.c:12062) as a library call.
+#include <string.h>
+
+#include "../../include/ries_b200.h"
+#include "host/ries_host.h"
+
+namespace ries {
+Engine* make_device_engine();
+unsigned long long device_engine_launches(Engine* e);
+}  // namespace ries
+
+static ries_run_stats g_last;
+
+extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
+  ries::Sink sink{out, ctx};
+  ries::Options opt;
+  ries::RunStats st;
+  int code = 0;
+  memset(&g_last, 0, sizeof(g_last));
+  ries::Engine* eng = 0;
+  try {
+    if (argc > 1) {
+      ries::parse_args(argc, argv, opt, sink);
+    } else { /* ries.c:12089 */
+      sink.printf("%s: Please specify a target number.\n\n", argc > 0 ? argv[0] : "ries");
+      ries::brief_help(sink);
+      throw ries::ExitRequest{1};
+    }
+    eng = ries::make_device_engine(); /* throws ExitRequest{3} without a GPU: there is no CPU path */
+    code = ries::run_search(opt, *eng, sink, &st);
+    g_last.kernel_launches = ries::device_engine_launches(eng);
+  } catch (const ries::ExitRequest& e) {
+    code = e.code;
+  }
+  delete eng;
+  g_last.lhs_expressions = st.lhs_gen; g_last.rhs_expressions = st.rhs_gen;
+  g_last.lhs_dead_ends = st.lhs_prune; g_last.rhs_dead_ends = st.rhs_prune;
+  g_last.lhs_distinct = st.lhs_insert; g_last.rhs_distinct = st.rhs_insert;
+  g_last.lhs_max_complexity = st.lmax; g_last.rhs_max_complexity = st.rmax;
+  g_last.passes = st.passes;
+  g_last.exit_code = code;
+  g_last.seconds = st.exec_seconds;
+  return code;
+}
+
+extern "C" void ries_last_stats(ries_run_stats* out) {
+  if (out) *out = g_last;
+}
+
+extern "C" const char* ries_engine_name(void) {
+  try {
+    ries::Engine* e = ries::make_device_engine();
+    delete e;
+    return "sm_100a";
+  } catch (...) {
+    return "unavailable: no CUDA device";
+  }
+}
