@@ -103,9 +103,9 @@ RIES_HD int exec_unary(const RiesParams& P, unsigned char op, bool do_dx, const 
       }
       a *= P.sincos_scale;
       if ((a > P.trig_max_arg) || (-a > P.trig_max_arg)) return ERR_EXEC_TRIG_RANGE;
-      rv = rm_sin(a);
+      double ca;
+      rm_sincos(a, &rv, &ca); /* gcc -O2 folds the reference's SIN(a)/COS(a) into one sincos() */
       if (fabs(rv) > P.k_sin_clip) return ERR_EXEC_TRIG_LOW_DX;
-      double ca = rm_cos(a);
       if (fabs(ca) < P.k_sig_loss) return ERR_EXEC_SIG_LOSS;
       if (fabs(rv) < (fabs(a) * P.k_sig_loss)) return ERR_EXEC_SIG_LOSS;
       if (do_dx) {
@@ -121,9 +121,9 @@ RIES_HD int exec_unary(const RiesParams& P, unsigned char op, bool do_dx, const 
       }
       a *= P.sincos_scale;
       if ((a > P.trig_max_arg) || (-a > P.trig_max_arg)) return ERR_EXEC_TRIG_RANGE;
-      rv = rm_cos(a);
+      double sa;
+      rm_sincos(a, &sa, &rv);
       if (fabs(rv) < (fabs(a) * P.k_sig_loss)) return ERR_EXEC_SIG_LOSS;
-      double sa = rm_sin(a);
       if (fabs(sa) < P.k_sig_loss) return ERR_EXEC_SIG_LOSS;
       if (fabs(rv) > P.k_sin_clip) return ERR_EXEC_TRIG_LOW_DX;
       if (do_dx) drv = 0.0 - (sa * P.sincos_scale * da);

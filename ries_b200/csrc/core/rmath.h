@@ -1,5 +1,5 @@
 // rmath: the seven libm entry points the search calls (ries.c:2666-2701: exp log pow sin cos tan
-// atan2), as ONE deterministic fp64 implementation compiled for both host and device.
+// atan2; sin+cos always come as one sincos call), as ONE deterministic fp64 implementation compiled for both host and device.
 //
 // The reference links glibc's libm (2.39 on this image; not part of /root/reference), and the value
 // table dedupes on `==` of doubles, so the device needs the same bits glibc produces.
@@ -31,8 +31,7 @@
 RIES_HD double rm_exp(double x) { return exp(x); }
 RIES_HD double rm_log(double x) { return log(x); }
 RIES_HD double rm_pow(double x, double y) { return pow(x, y); }
-RIES_HD double rm_sin(double x) { return sin(x); }
-RIES_HD double rm_cos(double x) { return cos(x); }
+RIES_HD void rm_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); } /* gcc: one sincos() */
 RIES_HD double rm_tan(double x) { return tan(x); }
 RIES_HD double rm_atan2(double y, double x) { return atan2(y, x); }
 #else

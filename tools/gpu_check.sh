@@ -15,7 +15,7 @@ while IFS= read -r line; do
   t1=$(date +%s.%N)
   a2=$(echo "$a" | sed -E 's/Time: [0-9.]+/Time: X/' | sed "s#$chk#ries#g")
   b2=$(echo "$b" | sed -E 's/Time: [0-9.]+/Time: X/' | sed "s#$gpu#ries#g")
-  dt=$(echo "$t1 - $t0" | bc)
+  dt=$(python3 -c "print(round($t1-$t0,2))")
   if [ "$a2" == "$b2" ]; then echo "SAME  (${dt}s) $line"; else echo "DIFF  (${dt}s) $line"; diff <(echo "$a2") <(echo "$b2") | head -12; fail=1; fi
 done < "$list"
 exit $fail
