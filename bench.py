@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""bench.py -- expressions evaluated/sec and time-to-full-report of the RIES search on B200.
+
+A "step" is one complete search (enumerate -> evaluate -> sort/dedupe/merge -> match/Newton -> report)
+through the reference-facing C ABI (`ries_main(argc, argv, write_cb)`, include/ries_b200.h), i.e. exactly
+the call the web worker makes (`callMain([...flags, target])`).  Nothing is reused between steps except
+device allocations: every step rebuilds the whole value table from scratch.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N independent targets)
+    python bench.py --impl reference          (the reference's own CPU implementation, oracle/_ref/ries)
+
+Default workload (N=1): `ries 2.5063141592653589 -l6 -F3`, the full-depth -l6 search BASELINE.json's metric
+is quoted on (1.45e8 expressions, 2.04e9 dead-ends, 3.23e7 table rows; fits one GPU).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_TARGET = "2.5063141592653589"
+DEFAULT_LEVEL = "6"
+# BASELINE.md config 5 distribution: f"{random.uniform(0,10):.6f}", seed 20261019 (first 8 targets)
+BATCH_SEED = 20261019
+
+# algorithmic bytes per survivor through the sort (read once + write once of a
+# 32-byte row) and per merged row (read old+new, write merged); flop weights per exec'd symbol.
+ROW_BYTES = 32
+SORT_BYTES_PER_KEY = 2 * ROW_BYTES
+MERGE_BYTES_PER_ROW = 2 * ROW_BYTES
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    for n, v in zip(names, parts[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def ref_binary():
+    for name in ("ries",):
+        p = os.path.join(ROOT, "oracle", "_ref", name)
+        if os.path.exists(p):
+            return p, "reference"
+    p = os.path.join(ROOT, "oracle", "_build", "ries_oracle")
+    return (p, "port") if os.path.exists(p) else (None, None)
+
+
+def parse_expressions(text):
+    m = re.search(r"expressions:\s+(\d+)\s+(\d+)\s+(\d+)", text)
+    return int(m.group(3)) if m else 0
+
+
+def run_cpu(binary, argv):
+    env = dict(os.environ, HOME="/nonexistent")
+    t0 = time.perf_counter()
+    r = subprocess.run([binary] + argv + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    return parse_expressions(r.stdout), dt
+
+
+def targets_for(n):
+    import random
+    rng = random.Random(BATCH_SEED)
+    out = []
+    while len(out) < n:
+        t = "%.6f" % rng.uniform(0, 10)
+        if float(t) != 0.0:
+            out.append(t)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--target", default=DEFAULT_TARGET)
+    ap.add_argument("--level", default=DEFAULT_LEVEL)
+    ap.add_argument("--cpu-level", default="4", help="level of the bounded CPU sample (same target)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world)
+    workload = "ries %s -l%s -F3" % (args.target, args.level)
+    sample_desc = ("the first pass-prefix of the same search: `ries %s -l%s` (identical pass sequence, stops at "
+                   "the -l%s expression budget)" % (args.target, args.cpu_level, args.cpu_level))
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        binary, kind = ref_binary()
+        if binary is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ries and oracle/_build/ries_oracle are both missing"}))
+            return 0
+        argv = [args.target, "-l" + args.cpu_level, "-F3"]
+        for _ in range(min(args.warmup, 1)):
+            run_cpu(binary, argv)
+        total_expr, total_t = 0, 0.0
+        for _ in range(args.steps):
+            n, dt = run_cpu(binary, argv)
+            total_expr += n
+            total_t += dt
+        v = total_expr / total_t
+        line = {
+            "impl": "reference", "metric": "expressions_evaluated_per_sec", "value": v, "unit": "expr/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample_desc},
+            "cpu_baseline": {"value": v, "unit": "expr/s", "cores": 1, "kind": kind, "sample": sample_desc},
+            "e2e": {"value": v, "unit": "expr/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["RIES_DEVICE"] = str(local_rank)
+    import ries_b200
+
+    if world > 1:
+        target = targets_for(world)[rank]  # independent targets: BASELINE config-5 style sharding
+    else:
+        target = args.target
+    argv = [target, "-l" + args.level, "-F3", "--no-slow-messages"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        t0 = time.perf_counter()
+        code, text = ries_b200.call_main(argv)
+        dt = time.perf_counter() - t0
+        st = ries_b200.last_stats()
+        assert code in (0, -9998), (code, text[-400:])
+        return dt, st, text
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_begin = time.perf_counter()
+    per_step = []
+    for _ in range(args.steps):
+        per_step.append(step())
+    barrier()
+    wall = time.perf_counter() - t_begin
+    clocks = sampler.stop()
+
+    exprs = sum(s[1]["lhs_expressions"] + s[1]["rhs_expressions"] for s in per_step)
+    dead = sum(s[1]["lhs_dead_ends"] + s[1]["rhs_dead_ends"] for s in per_step)
+    dev_ms = [sum(s[1]["stage_ms"][i] for s in per_step) for i in range(4)]
+    dev_launches = [sum(s[1]["stage_launches"][i] for s in per_step) for i in range(4)]
+    launches = sum(s[1]["kernel_launches"] for s in per_step)
+    h2d = sum(s[1]["h2d_bytes"] for s in per_step) / args.steps
+    d2h = sum(s[1]["d2h_bytes"] for s in per_step) / args.steps
+    sort_keys = sum(s[1]["sort_keys"] for s in per_step)
+    merge_rows = sum(s[1]["merge_rows"] for s in per_step)
+    nodes = sum(s[1]["expand_nodes"] for s in per_step)
+    dev_total_s = sum(dev_ms) / 1e3
+
+    # whole-job numbers: sum of units over ranks, max of time over ranks
+    if dist is not None:
+        t = torch.tensor([exprs, dead, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        tmax = torch.tensor([wall, dev_total_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        exprs_all, dead_all, launches_all = t.tolist()
+        wall_all, dev_all = tmax.tolist()
+    else:
+        exprs_all, dead_all, launches_all, wall_all, dev_all = exprs, dead, launches, wall, dev_total_s
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    hbm_peak, peak_kind = peaks()
+    # HBM-bound stages: [1] order+radix sort, [2] dedupe/match/merge
+    sort_bytes = sort_keys * SORT_BYTES_PER_KEY
+    merge_bytes = merge_rows * MERGE_BYTES_PER_ROW + merge_rows * ROW_BYTES  # merge + one neighbour-search read
+    stages = [
+        ("K2 order+radix sort (k_rs_hist/k_rs_scatter)", sort_bytes, dev_ms[1], dev_launches[1]),
+        ("K2/K3 classify+match+merge (k_classify/k_match/k_merge_*)", merge_bytes, dev_ms[2], dev_launches[2]),
+    ]
+    dom = max(stages, key=lambda s: s[2])
+    achieved = dom[1] / (dom[2] / 1e3) / 1e9 if dom[2] > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+        "algorithmic_bytes_per_step": dom[1] / args.steps, "launches_per_step": dom[3] / args.steps,
+        "avg_launch_ms": dom[2] / dom[3] if dom[3] else None,
+        "stage_ms_per_step": {"K1_enum_eval": dev_ms[0] / args.steps, "K2_sort": dev_ms[1] / args.steps,
+                              "K2K3_dedupe_match_merge": dev_ms[2] / args.steps, "K4_refine": dev_ms[3] / args.steps},
+        "note": "K1 is the fp64/latency-bound stage (no HBM roofline); see DESIGN.md section 6",
+    }
+
+    line = {
+        "metric": "expressions_evaluated_per_sec",
+        "value": exprs_all / dev_all if dev_all > 0 else 0.0,
+        "unit": "expr/s",
+        "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": workload if world == 1 else "ries <t_rank> -l%s -F3, one independent target per GPU (BASELINE config-5 distribution, seed %d)" % (args.level, BATCH_SEED),
+            "expressions_per_step": exprs_all / args.steps, "dead_ends_per_step": dead_all / args.steps,
+            "l2": "every step rebuilds all device data from scratch; working set (table + survivors + nodes) exceeds the 126 MB L2 at this level",
+            "value_is": "expressions / device-busy time (CUDA events over all stages); e2e is the same search timed around the C-ABI call",
+        },
+        "time_to_full_report_s": wall_all / args.steps,
+        "nodes_per_sec_e2e": (exprs_all + dead_all) / wall_all,
+        "e2e": {"value": exprs_all / wall_all, "unit": "expr/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "ries_main(argc, argv, write_cb) via ctypes"},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+
+    if not args.no_cpu_baseline and world == 1:
+        binary, kind = ref_binary()
+        if binary:
+            n, dt = run_cpu(binary, [args.target, "-l" + args.cpu_level, "-F3"])
+            line["cpu_baseline"] = {"value": n / dt, "unit": "expr/s", "cores": 1, "kind": kind, "sample": sample_desc,
+                                    "seconds": dt, "expressions": n}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -37,6 +37,14 @@ typedef struct ries_run_stats {
   int exit_code;
   double seconds;                           /* wall time inside ries_main */
   unsigned long long kernel_launches;      /* CUDA kernels this call launched */
+  unsigned long long h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host */
+  /* device time per stage from CUDA events on the engine's stream, milliseconds, and the launches in
+     each: [0] K1 enumerate+evaluate  [1] order + radix sort  [2] dedupe/match/merge  [3] Newton refine */
+  double stage_ms[4];
+  unsigned long long stage_launches[4];
+  unsigned long long sort_keys;            /* complete expressions that went through the radix sort */
+  unsigned long long merge_rows;           /* table rows written by the per-pass merges */
+  unsigned long long expand_nodes;         /* live prefixes evaluated by K1 */
 } ries_run_stats;
 void ries_last_stats(ries_run_stats *out);
 

@@ -21,6 +21,10 @@ class _Stats(ctypes.Structure):
         ("lhs_max_complexity", ctypes.c_int), ("rhs_max_complexity", ctypes.c_int),
         ("passes", ctypes.c_int), ("exit_code", ctypes.c_int),
         ("seconds", ctypes.c_double), ("kernel_launches", ctypes.c_ulonglong),
+        ("h2d_bytes", ctypes.c_ulonglong), ("d2h_bytes", ctypes.c_ulonglong),
+        ("stage_ms", ctypes.c_double * 4), ("stage_launches", ctypes.c_ulonglong * 4),
+        ("sort_keys", ctypes.c_ulonglong), ("merge_rows", ctypes.c_ulonglong),
+        ("expand_nodes", ctypes.c_ulonglong),
     ]
 
 
@@ -72,7 +76,11 @@ def run(target, *flags):
 def last_stats():
     s = _Stats()
     _load().ries_last_stats(ctypes.byref(s))
-    return {name: getattr(s, name) for name, _ in _Stats._fields_}
+    out = {}
+    for name, _ in _Stats._fields_:
+        v = getattr(s, name)
+        out[name] = list(v) if hasattr(v, "__len__") else v
+    return out
 
 
 def engine_name():

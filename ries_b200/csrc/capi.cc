@@ -6,10 +6,13 @@
 
 namespace ries {
 Engine* make_device_engine();
-unsigned long long device_engine_launches(Engine* e);
+void device_engine_report(Engine* e, DeviceReport* r);
 }  // namespace ries
 
 static ries_run_stats g_last;
+/* One engine per process, reused by successive ries_main() calls (the web worker calls callMain
+   repeatedly on one module instance, ries.worker.js:64-123): device buffers stay allocated. */
+static ries::Engine* g_engine = 0;
 
 extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
   ries::Sink sink{out, ctx};
@@ -17,7 +20,6 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
   ries::RunStats st;
   int code = 0;
   memset(&g_last, 0, sizeof(g_last));
-  ries::Engine* eng = 0;
   try {
     if (argc > 1) {
       ries::parse_args(argc, argv, opt, sink);
@@ -26,13 +28,22 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
       ries::brief_help(sink);
       throw ries::ExitRequest{1};
     }
-    eng = ries::make_device_engine(); /* throws ExitRequest{3} without a GPU: there is no CPU path */
-    code = ries::run_search(opt, *eng, sink, &st);
-    g_last.kernel_launches = ries::device_engine_launches(eng);
+    if (!g_engine) g_engine = ries::make_device_engine(); /* throws ExitRequest{3} without a GPU: no CPU path */
+    code = ries::run_search(opt, *g_engine, sink, &st);
   } catch (const ries::ExitRequest& e) {
     code = e.code;
   }
-  delete eng;
+  if (g_engine) {
+    ries::DeviceReport r;
+    ries::device_engine_report(g_engine, &r);
+    g_last.kernel_launches = r.kernel_launches;
+    g_last.h2d_bytes = r.h2d_bytes;
+    g_last.d2h_bytes = r.d2h_bytes;
+    for (int i = 0; i < 4; i++) { g_last.stage_ms[i] = r.stage_ms[i]; g_last.stage_launches[i] = r.stage_launches[i]; }
+    g_last.sort_keys = r.sort_keys;
+    g_last.merge_rows = r.merge_rows;
+    g_last.expand_nodes = r.expand_nodes;
+  }
   g_last.lhs_expressions = st.lhs_gen; g_last.rhs_expressions = st.rhs_gen;
   g_last.lhs_dead_ends = st.lhs_prune; g_last.rhs_dead_ends = st.rhs_prune;
   g_last.lhs_distinct = st.lhs_insert; g_last.rhs_distinct = st.rhs_insert;
@@ -49,8 +60,7 @@ extern "C" void ries_last_stats(ries_run_stats* out) {
 
 extern "C" const char* ries_engine_name(void) {
   try {
-    ries::Engine* e = ries::make_device_engine();
-    delete e;
+    if (!g_engine) g_engine = ries::make_device_engine();
     return "sm_100a";
   } catch (...) {
     return "unavailable: no CUDA device";

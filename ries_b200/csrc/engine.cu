@@ -607,6 +607,10 @@ class DeviceEngine : public Engine {
     cur_ = 0;
     last_nu_ = 0;
     kernel_launches = 0;
+    h2d_bytes = sizeof(P);
+    d2h_bytes = 0;
+    for (int i = 0; i < 4; i++) { stage_ms[i] = 0; stage_launches[i] = 0; }
+    sort_keys = merge_rows = expand_nodes = 0;
   }
 
   long inserted_before(uint32_t seq, bool inclusive) override {
@@ -633,9 +637,12 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMemcpyAsync(forms_.p, forms.data(), nforms * sizeof(FormDesc), cudaMemcpyHostToDevice, st_));
     form_first_.ensure(nforms); form_cnt_.ensure(nforms); form_base_.ensure(nforms);
 
+    h2d_bytes += nforms * sizeof(FormDesc);
     /* ---- phase A: K1, rerun with larger arenas on overflow ---- */
     while (true) {
       nodes_.ensure(nforms + 16);
+      cudaEvent_t ta = stage_begin();
+      unsigned long long l0 = kernel_launches;
       k_init_roots<<<(nforms + 255) / 256, 256, 0, st_>>>(nodes_.p, nforms, d_ctl_);
       kernel_launches++;
       for (int lvl = 0; lvl < max_len; lvl++) {
@@ -645,9 +652,11 @@ class DeviceEngine : public Engine {
         k_level_finish<<<1, 1024, 0, st_>>>(d_ctl_, tiles_.p, (u32)nodes_.cap, (u32)done_.cap);
         kernel_launches += 2;
       }
+      stage_end(ta, 0, l0);
       CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
       CUDA_CHECK(cudaStreamSynchronize(st_));
       CUDA_CHECK(cudaGetLastError());
+      d2h_bytes += sizeof(PassCtl);
       if (!(h_ctl_->overflow & 3)) break;
       /* grow (the counters say how much the level that overflowed needed; later levels may need
          more, so grow generously) and retry; the table has not been touched yet */
@@ -659,6 +668,7 @@ class DeviceEngine : public Engine {
       ensure_tiles();
     }
     const u32 n = h_ctl_->done_count;
+    expand_nodes += h_ctl_->node_count;
     out.generated = (double)n;
     out.dead_ends = (double)h_ctl_->dead;
     out.inserted = 0;
@@ -669,6 +679,9 @@ class DeviceEngine : public Engine {
     for (int b = 0; b < 2; b++) { keys_[b].ensure(n); idx_[b].ensure(n); }
     flag_.ensure(n); flag_scan_.ensure(n); gap_.ensure(n); uniq_seq_.ensure(n); uniq_gap_.ensure(n);
     const u32 nb256 = (n + 255) / 256;
+    cudaEvent_t tb = stage_begin();
+    unsigned long long l1 = kernel_launches;
+    sort_keys += n;
     CUDA_CHECK(cudaMemsetAsync(form_cnt_.p, 0, nforms * sizeof(u32), st_));
     CUDA_CHECK(cudaMemsetAsync(form_first_.p, 0, nforms * sizeof(u32), st_));
     k_form_bounds<<<nb256, 256, 0, st_>>>(done_form_.p, n, form_first_.p, form_cnt_.p);
@@ -691,8 +704,11 @@ class DeviceEngine : public Engine {
       src ^= 1;
     }
     const u32* sidx = idx_[src].p;
+    stage_end(tb, 1, l1);
 
     events_cap_check();
+    cudaEvent_t tc = stage_begin();
+    unsigned long long l2 = kernel_launches;
     k_classify<<<nb256, 256, 0, st_>>>(surv_.p, sidx, n, tval_[cur_].p, trow_[cur_].p, nt_, flag_.p, gap_.p,
                                       using_x, skip_exact ? 1 : 0, events_.p, (u32)events_.cap, d_ctl_);
     kernel_launches++;
@@ -701,6 +717,7 @@ class DeviceEngine : public Engine {
     kernel_launches++;
     CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
+    d2h_bytes += sizeof(PassCtl);
     const u32 nu = h_ctl_->n_uniq;
     out.inserted = (long)nu;
     last_nu_ = nu;
@@ -719,17 +736,24 @@ class DeviceEngine : public Engine {
         kernel_launches++;
       }
     }
+    if (nu) merge_rows += (unsigned long long)nt_ + nu;
+    stage_end(tc, 2, l2);
     /* events: count, (re)run on overflow is not needed -- cap is generous and checked */
     CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
+    d2h_bytes += sizeof(PassCtl);
     if (h_ctl_->overflow & 4) {
       fprintf(stderr, "ries_b200: candidate buffer overflow (%u events)\n", h_ctl_->n_events);
       abort();
     }
     const u32 ne = h_ctl_->n_events;
     if (ne) {
+      cudaEvent_t td = stage_begin();
+      unsigned long long l3 = kernel_launches;
       k_refine<<<(ne + 63) / 64, 64, 0, st_>>>(d_P_, events_.p, ne);
       kernel_launches++;
+      stage_end(td, 3, l3);
+      d2h_bytes += (unsigned long long)ne * sizeof(MatchEvent);
       if (ne > h_events_cap_) {
         if (h_events_) cudaFreeHost(h_events_);
         h_events_cap_ = std::max<size_t>(ne, h_events_cap_ * 2);
@@ -750,9 +774,51 @@ class DeviceEngine : public Engine {
   }
 
   unsigned long long kernel_launches = 0;
+  unsigned long long h2d_bytes = 0, d2h_bytes = 0;
+  /* device time per stage, CUDA events on the launching stream (ms): 0 K1 enumerate+evaluate,
+     1 order+radix sort, 2 classify/compact/match/merge, 3 refine */
+  double stage_ms[4] = {0, 0, 0, 0};
+  unsigned long long stage_launches[4] = {0, 0, 0, 0};
+  unsigned long long sort_keys = 0;      /* survivors that went through the radix sort */
+  unsigned long long merge_rows = 0;     /* rows written by the merges (old + new) */
+  unsigned long long expand_nodes = 0;   /* live prefixes expanded (= exec'd prefixes) */
   u32 table_rows() const { return nt_; }
+  void collect_stage_times() {
+    for (size_t i = 0; i < pend_.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, pend_[i].a, pend_[i].b);
+      stage_ms[pend_[i].stage] += ms;
+      ev_pool_.push_back(pend_[i].a);
+      ev_pool_.push_back(pend_[i].b);
+    }
+    pend_.clear();
+  }
 
  private:
+  struct Pend { cudaEvent_t a, b; int stage; };
+  std::vector<Pend> pend_;
+  std::vector<cudaEvent_t> ev_pool_;
+  cudaEvent_t get_event() {
+    if (ev_pool_.empty()) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      return e;
+    }
+    cudaEvent_t e = ev_pool_.back();
+    ev_pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t stage_begin() {
+    cudaEvent_t a = get_event();
+    CUDA_CHECK(cudaEventRecord(a, st_));
+    return a;
+  }
+  void stage_end(cudaEvent_t a, int stage, unsigned long long launches_before) {
+    cudaEvent_t b = get_event();
+    CUDA_CHECK(cudaEventRecord(b, st_));
+    pend_.push_back(Pend{a, b, stage});
+    stage_launches[stage] += kernel_launches - launches_before;
+  }
   void ensure_tiles() {
     size_t want = nodes_.cap / EXP_PARENTS + 2;
     if (want > tiles_.cap) {
@@ -813,6 +879,18 @@ class DeviceEngine : public Engine {
 };
 
 Engine* make_device_engine() { return new DeviceEngine(); }
-unsigned long long device_engine_launches(Engine* e) { return static_cast<DeviceEngine*>(e)->kernel_launches; }
+
+void device_engine_report(Engine* e, DeviceReport* r) {
+  DeviceEngine* d = static_cast<DeviceEngine*>(e);
+  d->collect_stage_times();
+  r->kernel_launches = d->kernel_launches;
+  r->h2d_bytes = d->h2d_bytes;
+  r->d2h_bytes = d->d2h_bytes;
+  for (int i = 0; i < 4; i++) { r->stage_ms[i] = d->stage_ms[i]; r->stage_launches[i] = d->stage_launches[i]; }
+  r->sort_keys = d->sort_keys;
+  r->merge_rows = d->merge_rows;
+  r->expand_nodes = d->expand_nodes;
+  r->table_rows = d->table_rows();
+}
 
 }  // namespace ries

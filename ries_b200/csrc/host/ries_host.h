@@ -126,6 +126,14 @@ struct RunStats {
   double exec_seconds = 0;
 };
 
+/* What the device engine measured during one search (CUDA events on its own stream). */
+struct DeviceReport {
+  unsigned long long kernel_launches, h2d_bytes, d2h_bytes;
+  double stage_ms[4];
+  unsigned long long stage_launches[4];
+  unsigned long long sort_keys, merge_rows, expand_nodes, table_rows;
+};
+
 /* main() after parse_args: the whole search.  Returns the process exit code. */
 int run_search(Options& opt, Engine& eng, const Sink& out, RunStats* stats_out);
 

@@ -1,0 +1,72 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against (a) the committed reference outputs,
+(b) the reference binaries run live on the box's CPU, (c) size-independent properties at full size."""
+import os
+import random
+import re
+
+import pytest
+
+from conftest import ROOT, golden_cases, golden_text, normalise, run_binary
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_run(args):
+    import ries_b200
+    code, text = ries_b200.call_main(list(args) + ["--no-slow-messages"])
+    shown = code & 0xff if code not in (0,) else 0
+    return normalise(text) + "exit=%d\n" % shown
+
+
+ALL_SMALL = golden_cases(big=False)
+BIG = golden_cases(big=True)
+
+
+@pytest.mark.parametrize("case", ALL_SMALL, ids=[c["name"] for c in ALL_SMALL])
+def test_gpu_matches_reference_goldens(product_lib, case):
+    """Byte-identical report (equations, counters, memory line, exit status) to unmodified ries.c."""
+    assert gpu_run(case["args"]) == golden_text(case["name"])
+
+
+@pytest.mark.parametrize("case", BIG, ids=[c["name"] for c in BIG])
+def test_gpu_matches_reference_goldens_full_size(product_lib, case):
+    """BASELINE configs at full size: -l6 (1.45e8 expressions), -i -l5, restricted -S -l5."""
+    assert gpu_run(case["args"]) == golden_text(case["name"])
+
+
+def test_gpu_matches_live_reference_on_random_targets(product_lib, oracle_build):
+    """Seeded random targets (BASELINE config-5 distribution) against the reference binary on this box."""
+    ref = os.path.join(oracle_build, "_ref", "ries")
+    if not os.path.exists(ref):
+        ref = os.path.join(oracle_build, "_build", "ries_oracle")
+    rng = random.Random(20261019)
+    for _ in range(6):
+        t = "%.6f" % rng.uniform(0, 10)
+        args = [t, "-l2", "-F3"]
+        assert gpu_run(args) == run_binary(ref, args), t
+
+
+def test_gpu_repeated_calls_are_independent(product_lib):
+    """callMain may be called repeatedly on one module instance (ries.worker.js:64-123)."""
+    a = gpu_run(["2.5063", "-l1", "-F3"])
+    b = gpu_run(["3.14159265358979", "-F3"])
+    c = gpu_run(["2.5063", "-l1", "-F3"])
+    assert a == c and a != b
+    assert b == golden_text("pi_l2_F3")
+
+
+def test_gpu_level_prefix_property(product_lib):
+    """A deeper level replays the shallower search first: every equation line of -l2 appears, in order, at
+    the start of the -l3 report (the level only moves the stopping budget, ries.c:12363-12367)."""
+    eq = lambda text: [l for l in text.splitlines() if " = " in l and "{" in l]
+    l2, l3 = eq(gpu_run(["2.5063", "-l2", "-F3"])), eq(gpu_run(["2.5063", "-l3", "-F3"]))
+    assert l2 and l3[:len(l2)] == l2
+
+
+def test_gpu_stats_are_consistent(product_lib):
+    import ries_b200
+    gpu_run(["2.5063", "-l3", "-F3"])
+    st = ries_b200.last_stats()
+    assert st["kernel_launches"] > 0
+    assert st["lhs_distinct"] <= st["lhs_expressions"] and st["rhs_distinct"] <= st["rhs_expressions"]
+    assert st["sort_keys"] == st["lhs_expressions"] + st["rhs_expressions"]

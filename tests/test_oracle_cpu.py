@@ -1,0 +1,52 @@
+"""CPU-only: the checkers against the reference's own outputs (tests/golden, made by tools/make_golden.py
+from the unmodified ries.c) and against each other."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT, golden_cases, golden_text, run_binary
+
+SMALL = [c for c in golden_cases(big=False) if c["name"] not in ("t25063_l4_F3",)]
+
+
+@pytest.mark.parametrize("case", SMALL, ids=[c["name"] for c in SMALL])
+def test_batch_emulation_matches_reference_goldens(oracle_build, case):
+    """The batch formulation (generate pass -> stable sort -> dedupe -> merge -> gap-local neighbour test ->
+    ordered replay) driven on the CPU with rmath must print exactly what the streaming reference prints."""
+    got = run_binary(os.path.join(oracle_build, "_build", "ries_emul"), case["args"])
+    assert got == golden_text(case["name"])
+
+
+@pytest.mark.parametrize("case", SMALL, ids=[c["name"] for c in SMALL])
+def test_c_restatement_matches_reference_goldens(oracle_build, case):
+    """oracle/ries_oracle.c (streaming restatement, stock libm) is pinned to the reference's outputs."""
+    got = run_binary(os.path.join(oracle_build, "_build", "ries_oracle"), case["args"])
+    assert got == golden_text(case["name"])
+
+
+def test_l4_headline_config(oracle_build):
+    """BASELINE config 2 (ries 2.5063 -l4): emulation with rmath == unmodified reference, all 22 equations and
+    every counter of the stats block."""
+    case = [c for c in golden_cases() if c["name"] == "t25063_l4_F3"][0]
+    got = run_binary(os.path.join(oracle_build, "_build", "ries_emul"), case["args"])
+    assert got == golden_text(case["name"])
+    assert "8948692" in got and "127357792" in got and "2635817" in got  # SURVEY section 8(c) KATs
+
+
+@pytest.mark.parametrize("func", ["exp", "log", "pow", "sincos", "tan", "atan2"])
+def test_rmath_bit_exact_vs_platform_libm(oracle_build, func):
+    """rmath must reproduce glibc's libm bit for bit on the ranges exec() can reach (and well beyond)."""
+    r = subprocess.run([os.path.join(oracle_build, "_build", "rmath_diff"), func, "3000000", "11"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert ": 0 / 3000000 mismatches" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ries_rm")), reason="no reference build")
+@pytest.mark.parametrize("args", [["2.5063", "-l2", "-F3"], ["0.5772156649", "-l2", "-F0"], ["19.99", "-l2", "-F3"]])
+def test_reference_with_rmath_equals_reference_with_glibc(oracle_build, args):
+    """The unmodified reference source linked against rmath prints what it prints with glibc."""
+    a = run_binary(os.path.join(oracle_build, "_ref", "ries"), args)
+    b = run_binary(os.path.join(oracle_build, "_ref", "ries_rm"), args)
+    assert a == b
