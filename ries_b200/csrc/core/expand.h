@@ -52,30 +52,32 @@ RIES_HD int prefix_attrs(const RiesParams& P, const FormDesc& F, const Node& par
   return atts;
 }
 
-/* `nodes` is the pass's node arena (parents of every level stay resident for `below` links);
-   `par_idx` is the parent's own index in it. */
-RIES_HD int expand_one(const RiesParams& P, const FormDesc& F, const Node* nodes, const Node& par,
-                       uint32_t par_idx, int slot, int atts, int using_x, int e_minw, int e_maxw,
-                       Node& child) {
+/* Symbol-append tests of ge_2's loop, in the reference's order (ries.c:9401-9445): complexity bounds,
+   rule mask, LHS-starts-with-x, -O symbol count.  false = one dead-end. */
+RIES_HD bool expand_tests(const RiesParams& P, const FormDesc& F, const Node& par, int slot, int atts,
+                          int using_x, int e_minw, int e_maxw) {
   int ip = par.len;
-  int cls = F.cls[ip];
-  if (slot >= P.cls_n[cls]) return OUT_NONE;
-  int g = P.trial[cls][slot];
-  unsigned char sym = P.sym_char[g];
-
-  /* symbol-append loop tests, in the reference's order (9401-9445) */
+  int g = P.trial[F.cls[ip]][slot];
   int t_cpx = par.cplx + P.sym_wgt[g];
-  if (t_cpx + F.rminw[ip + 1] > e_maxw) return OUT_DEAD;
-  if (t_cpx + F.rmaxw[ip + 1] < e_minw) return OUT_DEAD;
-  if (atts & P.sym_mask[g]) return OUT_DEAD;
-  if (using_x && (ip == 0) && (sym != 'x')) return OUT_DEAD;
+  if (t_cpx + F.rminw[ip + 1] > e_maxw) return false;
+  if (t_cpx + F.rmaxw[ip + 1] < e_minw) return false;
+  if (atts & P.sym_mask[g]) return false;
+  if (using_x && (ip == 0) && (P.sym_char[g] != 'x')) return false;
   if (P.sym_alwd[g] < RIES_MAX_ELEN) {
     int ct = 0;
     for (int i = 0; i < ip; i++) ct += (sym_get(par.sym, i) == (unsigned)(g + 1));
-    if (ct >= P.sym_alwd[g]) return OUT_DEAD;
+    if (ct >= P.sym_alwd[g]) return false;
   }
+  return true;
+}
 
-  /* exec the new symbol on the cactus stack (child's ge_2 entry, 8942-8954) */
+/* exec of the chosen symbol on the cactus stack (the child's ge_2 entry, 8942-8954), the value prunes
+   (8962-9076) and the complete-expression tests (9085-9139).  `nodes` is the pass's node arena
+   (parents of every level stay resident for `below` links); `par_idx` is the parent's own index.
+   Fills only the evaluation part of `child` (val, der, tag, below, sp). */
+RIES_HD int expand_exec(const RiesParams& P, int cls, int g, bool complete, const Node* nodes,
+                        const Node& par, uint32_t par_idx, int using_x, Node& child) {
+  unsigned char sym = P.sym_char[g];
   Val r;
   int err;
   uint32_t below;
@@ -110,21 +112,12 @@ RIES_HD int expand_one(const RiesParams& P, const FormDesc& F, const Node* nodes
     if ((r.d != 0.0) && (fabs(r.d) / (1.0 + fabs(r.v)) < P.k_vanished_dx)) return OUT_DEAD;
     if ((sp == 1) && (fabs(r.d) / (1.0 + fabs(r.v)) < P.k_vanished_dx)) return OUT_DEAD;
   }
-
   child.val = r.v;
   child.der = r.d;
-  child.sym = par.sym;
-  sym_set(child.sym, ip, (unsigned)(g + 1));
-  child.below = below;
-  child.form = par.form;
-  child.cplx = (int16_t)t_cpx;
   child.tag = (uint8_t)r.tag;
-  child.len = (uint8_t)(ip + 1);
+  child.below = below;
   child.sp = (uint8_t)sp;
-  child.pad0 = 0;
-  child.pad1 = 0;
-
-  if (ip + 1 >= F.flen) {
+  if (complete) {
     /* complete expression (9085-9139) */
     if (using_x && (fabs(r.d) < P.k_vanished_dx)) return OUT_DEAD;
     if (r.v < P.min_equ_val) return OUT_DEAD;
@@ -132,4 +125,30 @@ RIES_HD int expand_one(const RiesParams& P, const FormDesc& F, const Node* nodes
     return OUT_DONE;
   }
   return OUT_LIVE;
+}
+
+/* The bookkeeping part of a child: symbols, form, complexity, length. */
+RIES_HD void expand_finish(const RiesParams& P, const Node& par, int g, Node& child) {
+  child.sym = par.sym;
+  sym_set(child.sym, par.len, (unsigned)(g + 1));
+  child.form = par.form;
+  child.cplx = (int16_t)(par.cplx + P.sym_wgt[g]);
+  child.len = (uint8_t)(par.len + 1);
+  child.pad0 = 0;
+  child.pad1 = 0;
+}
+
+/* One (prefix, slot) pair end to end (used by the CPU emulation; the kernel runs the three parts in
+   separate phases so that threads can be regrouped by symbol in between). */
+RIES_HD int expand_one(const RiesParams& P, const FormDesc& F, const Node* nodes, const Node& par,
+                       uint32_t par_idx, int slot, int atts, int using_x, int e_minw, int e_maxw,
+                       Node& child) {
+  int ip = par.len;
+  int cls = F.cls[ip];
+  if (slot >= P.cls_n[cls]) return OUT_NONE;
+  if (!expand_tests(P, F, par, slot, atts, using_x, e_minw, e_maxw)) return OUT_DEAD;
+  int g = P.trial[cls][slot];
+  int oc = expand_exec(P, cls, g, ip + 1 >= F.flen, nodes, par, par_idx, using_x, child);
+  if (oc == OUT_LIVE || oc == OUT_DONE) expand_finish(P, par, g, child);
+  return oc;
 }

@@ -57,8 +57,22 @@ struct PassCtl {          /* lives in device memory, mirrored to pinned host mem
 
 /* ---------------------------------------------------------------- K1: enumerate+evaluate - */
 
+/* K1 works on tiles of 256 consecutive live prefixes (one block per tile at a time):
+     phase 1  thread = prefix: the integer symbol-append tests for all candidate symbols -> bit mask
+     phase 2  the (prefix, symbol) pairs that passed are listed in shared memory GROUPED BY SYMBOL SLOT
+     phase 3  thread = listed pair: exec + value prunes; warps are (almost) operator-uniform
+     phase 4  ordered append: children land in (prefix, symbol) order = the reference's DFS order */
 #define EXP_THREADS 256
-#define EXP_PARENTS (EXP_THREADS / RIES_SLOTS)
+#define EXP_PARENTS 256
+#define EXP_MAX_ITEMS (EXP_PARENTS * RIES_SLOTS)
+#define IT_LIVE 0x1000u
+#define IT_DONE 0x2000u
+
+struct __attribute__((aligned(8))) Staged { /* a child between phase 3 and phase 4 (L2-resident scratch) */
+  double val, der;
+  u32 below;
+  unsigned char tag, sp, pad0, pad1;
+};
 
 #define TS_AGG (1ull << 62)
 #define TS_INC (2ull << 62)
@@ -130,11 +144,17 @@ __device__ __forceinline__ void tile_lookback(volatile u64* state, u32 tile, u32
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, Node* nodes,
          Row* done, uint16_t* done_form, u32 cap_nodes, u32 cap_done, PassCtl* ctl,
-         volatile u64* tile_state, int using_x, int cplx) {
+         volatile u64* tile_state, Staged* staged_all, int using_x, int cplx) {
   __shared__ RiesParams P;
-  __shared__ u32 s_wlive[EXP_THREADS / 32], s_wdone[EXP_THREADS / 32];
-  __shared__ u32 s_live_base, s_done_base;
-  __shared__ u32 s_dead;
+  __shared__ Node s_par[EXP_PARENTS];
+  __shared__ unsigned short s_item[EXP_MAX_ITEMS];
+  __shared__ u32 s_live[EXP_PARENTS], s_done[EXP_PARENTS];   /* per prefix: bit per slot */
+  __shared__ u32 s_lbase[EXP_PARENTS], s_dbase[EXP_PARENTS]; /* per prefix: exclusive child offsets */
+  __shared__ unsigned char s_cls[EXP_PARENTS], s_complete[EXP_PARENTS];
+  __shared__ u32 s_wcnt[EXP_THREADS / 32][RIES_SLOTS];
+  __shared__ u32 s_slot_base[RIES_SLOTS];
+  __shared__ u32 s_wl[EXP_THREADS / 32], s_wd[EXP_THREADS / 32];
+  __shared__ u32 s_total, s_live_base, s_done_base, s_dead;
   {
     const u32* src = (const u32*)gP;
     u32* dst = (u32*)&P;
@@ -146,54 +166,132 @@ k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, 
   const u32 done_base0 = ctl->done_count; /* read-only during this launch (updated by k_level_finish) */
   const u32 n = lvl_end - lvl_begin;
   const u32 ntiles = (n + EXP_PARENTS - 1) / EXP_PARENTS;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = (1u << lane) - 1;
+  Staged* staged = staged_all + (size_t)blockIdx.x * EXP_MAX_ITEMS;
   u32 my_dead = 0;
 
   for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const u32 p = lvl_begin + tile * EXP_PARENTS + (threadIdx.x / RIES_SLOTS);
-    const int slot = threadIdx.x % RIES_SLOTS;
-    int oc = OUT_NONE;
-    Node child;
-    if (p < lvl_end) {
-      const Node par = nodes[p];
-      const FormDesc& F = forms[par.form];
-      int atts = prefix_attrs(P, F, par, using_x);
-      oc = expand_one(P, F, nodes, par, p, slot, atts, using_x, cplx, cplx, child);
+    const u32 p0 = lvl_begin + tile * EXP_PARENTS;
+    /* ---- phase 1: integer tests, one thread per prefix ---- */
+    u32 mask = 0;
+    {
+      const u32 p = p0 + tid;
+      if (p < lvl_end) {
+        const Node par = nodes[p];
+        s_par[tid] = par;
+        const FormDesc& F = forms[par.form];
+        const int cls = F.cls[par.len];
+        const int ns = P.cls_n[cls];
+        const int atts = prefix_attrs(P, F, par, using_x);
+        for (int k = 0; k < ns; k++) {
+          if (expand_tests(P, F, par, k, atts, using_x, cplx, cplx)) mask |= 1u << k;
+          else my_dead++;
+        }
+        s_cls[tid] = (unsigned char)cls;
+        s_complete[tid] = (unsigned char)(par.len + 1 >= F.flen);
+      }
+      s_live[tid] = 0;
+      s_done[tid] = 0;
     }
-    my_dead += (oc == OUT_DEAD);
-    const u32 live_m = __ballot_sync(0xffffffffu, oc == OUT_LIVE);
-    const u32 done_m = __ballot_sync(0xffffffffu, oc == OUT_DONE);
-    if (lane == 0) { s_wlive[warp] = __popc(live_m); s_wdone[warp] = __popc(done_m); }
-    __syncthreads();
-    if (warp == 0) {
-      u32 la = 0, da = 0;
-      for (int w = 0; w < EXP_THREADS / 32; w++) { la += s_wlive[w]; da += s_wdone[w]; }
-      u32 le, de;
-      tile_lookback(tile_state, tile, la, da, le, de);
-      if (lane == 0) { s_live_base = le; s_done_base = de; }
+    /* ---- phase 2: list the surviving pairs grouped by slot ---- */
+#pragma unroll
+    for (int k = 0; k < RIES_SLOTS; k++) {
+      u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
+      if (lane == 0) s_wcnt[warp][k] = __popc(b);
     }
     __syncthreads();
-    u32 lrank = s_live_base, drank = s_done_base;
-    for (u32 w = 0; w < warp; w++) { lrank += s_wlive[w]; drank += s_wdone[w]; }
-    const u32 lt = (1u << lane) - 1;
-    if (oc == OUT_LIVE) {
-      u32 pos = lvl_end + lrank + __popc(live_m & lt);
-      if (pos < cap_nodes) nodes[pos] = child;
-    } else if (oc == OUT_DONE) {
-      u32 pos = done_base0 + drank + __popc(done_m & lt);
-      if (pos < cap_done) {
-        Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
-        done[pos] = r;
-        done_form[pos] = child.form;
+    if (tid < RIES_SLOTS) { /* per slot: exclusive prefix over warps, and the slot's total */
+      u32 run = 0;
+      for (int w = 0; w < EXP_THREADS / 32; w++) { u32 c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+      s_slot_base[tid] = run;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      u32 run = 0;
+      for (int k = 0; k < RIES_SLOTS; k++) { u32 c = s_slot_base[k]; s_slot_base[k] = run; run += c; }
+      s_total = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RIES_SLOTS; k++) {
+      u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
+      if ((mask >> k) & 1u) s_item[s_slot_base[k] + s_wcnt[warp][k] + __popc(b & lt)] = (unsigned short)((tid << 4) | k);
+    }
+    __syncthreads();
+    const u32 T = s_total;
+    /* ---- phase 3: exec + value prunes, one thread per listed pair ---- */
+    for (u32 i = tid; i < T; i += EXP_THREADS) {
+      const u32 it = s_item[i];
+      const u32 pl = it >> 4, k = it & 15u;
+      const int cls = s_cls[pl];
+      const int g = P.trial[cls][k];
+      Node child;
+      int oc = expand_exec(P, cls, g, s_complete[pl] != 0, nodes, s_par[pl], p0 + pl, using_x, child);
+      if (oc == OUT_DEAD) my_dead++;
+      else if (oc == OUT_LIVE || oc == OUT_DONE) {
+        Staged st;
+        st.val = child.val; st.der = child.der; st.below = child.below; st.tag = child.tag; st.sp = child.sp;
+        st.pad0 = 0; st.pad1 = 0;
+        staged[i] = st;
+        if (oc == OUT_LIVE) { atomicOr(&s_live[pl], 1u << k); s_item[i] = (unsigned short)(it | IT_LIVE); }
+        else { atomicOr(&s_done[pl], 1u << k); s_item[i] = (unsigned short)(it | IT_DONE); }
       }
     }
-    __syncthreads(); /* s_w* reused by the next tile */
+    __syncthreads();
+    /* ---- phase 4: ordered append ---- */
+    {
+      u32 nl = __popc(s_live[tid]), nd = __popc(s_done[tid]);
+      u32 il = nl, id = nd;
+      for (int o = 1; o < 32; o <<= 1) {
+        u32 a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, id, o);
+        if (lane >= (u32)o) { il += a; id += b; }
+      }
+      if (lane == 31) { s_wl[warp] = il; s_wd[warp] = id; }
+      __syncthreads();
+      u32 wl = 0, wd = 0;
+      for (u32 w = 0; w < warp; w++) { wl += s_wl[w]; wd += s_wd[w]; }
+      s_lbase[tid] = wl + il - nl;
+      s_dbase[tid] = wd + id - nd;
+      if (warp == 0) {
+        u32 la = 0, da = 0;
+        for (int w = 0; w < EXP_THREADS / 32; w++) { la += s_wl[w]; da += s_wd[w]; }
+        u32 le, de;
+        tile_lookback(tile_state, tile, la, da, le, de);
+        if (lane == 0) { s_live_base = le; s_done_base = de; }
+      }
+      __syncthreads();
+    }
+    for (u32 i = tid; i < T; i += EXP_THREADS) {
+      const u32 it = s_item[i];
+      if (!(it & (IT_LIVE | IT_DONE))) continue;
+      const u32 pl = (it >> 4) & 255u, k = it & 15u;
+      const Node& par = s_par[pl];
+      const int g = P.trial[s_cls[pl]][k];
+      const Staged st = staged[i];
+      Node child;
+      child.val = st.val; child.der = st.der; child.below = st.below; child.tag = st.tag; child.sp = st.sp;
+      expand_finish(P, par, g, child);
+      const u32 below_k = (1u << k) - 1;
+      if (it & IT_LIVE) {
+        u32 pos = lvl_end + s_live_base + s_lbase[pl] + __popc(s_live[pl] & below_k);
+        if (pos < cap_nodes) nodes[pos] = child;
+      } else {
+        u32 pos = done_base0 + s_done_base + s_dbase[pl] + __popc(s_done[pl] & below_k);
+        if (pos < cap_done) {
+          Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
+          done[pos] = r;
+          done_form[pos] = child.form;
+        }
+      }
+    }
+    __syncthreads(); /* shared tile state is reused by the next tile */
   }
   /* block-level dead-end count -> one atomic per block */
   for (int o = 16; o > 0; o >>= 1) my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
   if (lane == 0 && my_dead) atomicAdd(&s_dead, my_dead);
   __syncthreads();
-  if (threadIdx.x == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
+  if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
 }
 
 /* After a level: advance the frontier, fold the level's totals, clear the tile states it used. */
@@ -583,6 +681,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, EXP_THREADS, 0));
     if (occ < 1) occ = 1;
     expand_grid_ = (u32)(num_sms_ * occ);
+    staged_.ensure((size_t)expand_grid_ * EXP_MAX_ITEMS);
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
     CUDA_CHECK(cudaMalloc(&d_ctl_, sizeof(PassCtl)));
     CUDA_CHECK(cudaMallocHost(&h_ctl_, sizeof(PassCtl)));
@@ -648,7 +747,7 @@ class DeviceEngine : public Engine {
       for (int lvl = 0; lvl < max_len; lvl++) {
         k_expand<<<expand_grid_, EXP_THREADS, 0, st_>>>(d_P_, forms_.p, nodes_.p, done_.p, done_form_.p,
                                                        (u32)nodes_.cap, (u32)done_.cap, d_ctl_,
-                                                       (volatile u64*)tiles_.p, using_x, cplx);
+                                                       (volatile u64*)tiles_.p, staged_.p, using_x, cplx);
         k_level_finish<<<1, 1024, 0, st_>>>(d_ctl_, tiles_.p, (u32)nodes_.cap, (u32)done_.cap);
         kernel_launches += 2;
       }
@@ -862,6 +961,7 @@ class DeviceEngine : public Engine {
   DevBuf<Row> done_, surv_;
   DevBuf<uint16_t> done_form_;
   DevBuf<u64> tiles_;
+  DevBuf<Staged> staged_;
   DevBuf<u32> form_first_, form_cnt_, form_base_;
   DevBuf<u64> keys_[2];
   DevBuf<u32> idx_[2];
