@@ -438,40 +438,112 @@ k_scan_apply(const u32* in, u32* out, u32 n, const u32* sums_excl, u32* total_ou
 }
 
 /* ---------------------------------------------------------------- K2: radix sort --------- */
+/* Stable LSD radix sort of (u64 key, u32 payload), 8 digits of 8 bits, "onesweep" style: ONE pass over
+   the keys builds all eight digit histograms; each digit pass is then a single kernel in which every
+   2048-key chunk gets its per-digit output offsets by decoupled look-back over the chunks before it
+   (chunks are taken in ticket order, so equal keys keep their input order = insertion order). */
 #define RS_THREADS 256
 #define RS_ITEMS 8
 #define RS_CHUNK (RS_THREADS * RS_ITEMS)
+#define RS_FLAG_AGG 1ull
+#define RS_FLAG_INC 2ull
+
+struct SortCtl {
+  u32 ghist[8][256];
+  u32 ticket[8];
+};
 
 __global__ void __launch_bounds__(RS_THREADS)
-k_rs_hist(const u64* __restrict__ keys, u32 n, int shift, u32* hist, u32 nblocks) {
-  __shared__ u32 s_h[256];
-  s_h[threadIdx.x] = 0;
+k_rs_hist_all(const u64* __restrict__ keys, u32 n, SortCtl* ctl) {
+  __shared__ u32 s_h[8][256];
+  for (int d = 0; d < 8; d++) s_h[d][threadIdx.x] = 0;
   __syncthreads();
-  u32 base = blockIdx.x * RS_CHUNK;
-  for (int r = 0; r < RS_ITEMS; r++) {
-    u32 i = base + r * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&s_h[(u32)(keys[i] >> shift) & 255u], 1u);
+  for (u32 base = blockIdx.x * RS_CHUNK; base < n; base += gridDim.x * RS_CHUNK) {
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+      u32 i = base + r * RS_THREADS + threadIdx.x;
+      if (i < n) {
+        u64 k = keys[i];
+#pragma unroll
+        for (int d = 0; d < 8; d++) atomicAdd(&s_h[d][(u32)(k >> (8 * d)) & 255u], 1u);
+      }
+    }
   }
   __syncthreads();
-  hist[threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+  for (int d = 0; d < 8; d++) {
+    u32 c = s_h[d][threadIdx.x];
+    if (c) atomicAdd(&ctl->ghist[d][threadIdx.x], c);
+  }
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-k_rs_scatter(const u64* __restrict__ keys_in, const u32* __restrict__ idx_in, u64* keys_out, u32* idx_out,
-             u32 n, int shift, const u32* __restrict__ hist, u32 nblocks) {
+k_rs_onesweep(const u64* __restrict__ keys_in, const u32* __restrict__ idx_in, u64* keys_out, u32* idx_out,
+              u32 n, int pass, SortCtl* ctl, volatile u64* state, u32 epoch) {
   __shared__ u32 s_off[256];
+  __shared__ u32 s_scan[256];
   __shared__ u32 s_wcnt[RS_THREADS / 32][256];
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  s_off[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
-  for (int w = 0; w < RS_THREADS / 32; w++) s_wcnt[w][threadIdx.x] = 0;
+  __shared__ u32 s_chunk;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int shift = pass * 8;
+  if (tid == 0) s_chunk = atomicAdd(&ctl->ticket[pass], 1u);
+  /* exclusive scan of the digit's global histogram (256 bins, Hillis-Steele in shared memory) */
+  u32 mine = ctl->ghist[pass][tid];
+  s_scan[tid] = mine;
+  for (int w = 0; w < RS_THREADS / 32; w++) s_wcnt[w][tid] = 0;
+  s_off[tid] = 0;
   __syncthreads();
-  u32 base = blockIdx.x * RS_CHUNK;
+  for (u32 o = 1; o < 256; o <<= 1) {
+    u32 v = (tid >= o) ? s_scan[tid - o] : 0;
+    __syncthreads();
+    s_scan[tid] += v;
+    __syncthreads();
+  }
+  const u32 gbase = s_scan[tid] - mine;
+  const u32 chunk = s_chunk;
+  const u32 base = chunk * RS_CHUNK;
+
+  /* local histogram of this chunk */
+  u64 key[RS_ITEMS];
+  u32 pay[RS_ITEMS];
+#pragma unroll
   for (int r = 0; r < RS_ITEMS; r++) {
-    u32 i = base + r * RS_THREADS + threadIdx.x;
+    u32 i = base + r * RS_THREADS + tid;
     bool valid = i < n;
-    u64 key = valid ? keys_in[i] : 0;
-    u32 pay = valid ? idx_in[i] : 0;
-    u32 d = (u32)(key >> shift) & 255u;
+    key[r] = valid ? keys_in[i] : 0;
+    pay[r] = valid ? idx_in[i] : 0;
+    if (valid) atomicAdd(&s_off[(u32)(key[r] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  const u32 local = s_off[tid];
+  /* decoupled look-back for bin `tid` over the chunks before this one */
+  {
+    volatile u64* st = state + (size_t)chunk * 256 + tid;
+    const u64 tag = (u64)epoch << 34;
+    u32 ex = 0;
+    if (chunk == 0) {
+      *st = tag | (RS_FLAG_INC << 32) | local;
+    } else {
+      *st = tag | (RS_FLAG_AGG << 32) | local;
+      int c = (int)chunk - 1;
+      while (c >= 0) {
+        u64 w;
+        do { w = state[(size_t)c * 256 + tid]; } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
+        ex += (u32)w;
+        if (((w >> 32) & 3ull) == RS_FLAG_INC) break;
+        c--;
+      }
+      *st = tag | (RS_FLAG_INC << 32) | (u64)(ex + local);
+    }
+    __syncthreads();
+    s_off[tid] = gbase + ex;
+  }
+  __syncthreads();
+  /* stable scatter: rows of 256 keys in order; inside a row, rank by (warp, lane) */
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    u32 i = base + r * RS_THREADS + tid;
+    bool valid = i < n;
+    u32 d = (u32)(key[r] >> shift) & 255u;
     u32 vmask = __ballot_sync(0xffffffffu, valid);
     u32 peers = 0, rank = 0;
     bool leader = false;
@@ -492,7 +564,7 @@ k_rs_scatter(const u64* __restrict__ keys_in, const u32* __restrict__ idx_in, u6
       atomicAdd(&s_off[d], (u32)__popc(peers));
       s_wcnt[warp][d] = 0;
     }
-    if (valid) { keys_out[dest] = key; idx_out[dest] = pay; }
+    if (valid) { keys_out[dest] = key[r]; idx_out[dest] = pay[r]; }
     __syncthreads();
   }
 }
@@ -684,10 +756,13 @@ class DeviceEngine : public Engine {
     staged_.ensure((size_t)expand_grid_ * EXP_MAX_ITEMS);
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
     CUDA_CHECK(cudaMalloc(&d_ctl_, sizeof(PassCtl)));
+    CUDA_CHECK(cudaMalloc(&d_sortctl_, sizeof(SortCtl)));
     CUDA_CHECK(cudaMallocHost(&h_ctl_, sizeof(PassCtl)));
-    nodes_.ensure(1u << 20);
-    done_.ensure(1u << 20);
-    done_form_.ensure(1u << 20);
+    const char* arena_env = getenv("RIES_ARENA_CAP"); /* test hook: start tiny to exercise overflow-and-rerun */
+    const size_t arena0 = arena_env ? (size_t)atoi(arena_env) : (size_t)(1u << 20);
+    nodes_.ensure(arena0);
+    done_.ensure(arena0);
+    done_form_.ensure(arena0);
     events_.ensure(1u << 14);
     ensure_tiles();
   }
@@ -789,16 +864,22 @@ class DeviceEngine : public Engine {
                                      keys_[0].p, idx_[0].p);
     kernel_launches += 3;
 
-    /* K2: 8 x 8-bit stable LSD passes */
+    /* K2: one histogram pass + 8 stable onesweep digit passes */
     const u32 rs_blocks = (n + RS_CHUNK - 1) / RS_CHUNK;
-    hist_.ensure((size_t)256 * rs_blocks);
+    rs_state_.ensure((size_t)rs_blocks * 256);
+    if (rs_state_.cap != rs_state_zeroed_) { /* fresh allocation: stale bits must not look like an epoch */
+      CUDA_CHECK(cudaMemsetAsync(rs_state_.p, 0, rs_state_.cap * sizeof(u64), st_));
+      rs_state_zeroed_ = rs_state_.cap;
+    }
+    CUDA_CHECK(cudaMemsetAsync(d_sortctl_, 0, sizeof(SortCtl), st_));
+    k_rs_hist_all<<<std::min<u32>(rs_blocks, (u32)num_sms_ * 4), RS_THREADS, 0, st_>>>(keys_[0].p, n, d_sortctl_);
+    kernel_launches++;
     int src = 0;
     for (int pass = 0; pass < 8; pass++) {
-      k_rs_hist<<<rs_blocks, RS_THREADS, 0, st_>>>(keys_[src].p, n, pass * 8, hist_.p, rs_blocks);
-      kernel_launches++;
-      exclusive_scan(hist_.p, hist_.p, 256 * rs_blocks, 0);
-      k_rs_scatter<<<rs_blocks, RS_THREADS, 0, st_>>>(keys_[src].p, idx_[src].p, keys_[src ^ 1].p,
-                                                     idx_[src ^ 1].p, n, pass * 8, hist_.p, rs_blocks);
+      rs_epoch_ = (rs_epoch_ + 1) & 0x3fffffffu;
+      if (rs_epoch_ == 0) rs_epoch_ = 1;
+      k_rs_onesweep<<<rs_blocks, RS_THREADS, 0, st_>>>(keys_[src].p, idx_[src].p, keys_[src ^ 1].p, idx_[src ^ 1].p, n,
+                                                       pass, d_sortctl_, (volatile u64*)rs_state_.p, rs_epoch_);
       kernel_launches++;
       src ^= 1;
     }
@@ -841,9 +922,23 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
     d2h_bytes += sizeof(PassCtl);
-    if (h_ctl_->overflow & 4) {
-      fprintf(stderr, "ries_b200: candidate buffer overflow (%u events)\n", h_ctl_->n_events);
-      abort();
+    while (h_ctl_->overflow & 4) {
+      /* more candidates than the buffer holds (huge --max-match-distance, or -i with many exact hits):
+         grow it and re-emit; the old table is still intact (ping-pong) and flags/gaps are unchanged */
+      events_.ensure((size_t)h_ctl_->n_events + 1024);
+      CUDA_CHECK(cudaMemsetAsync(&d_ctl_->n_events, 0, sizeof(u32), st_));
+      CUDA_CHECK(cudaMemsetAsync(&d_ctl_->overflow, 0, sizeof(u32), st_));
+      k_classify<<<nb256, 256, 0, st_>>>(surv_.p, sidx, n, tval_[cur_].p, trow_[cur_].p, nt_, flag_.p, gap_.p,
+                                        using_x, skip_exact ? 1 : 0, events_.p, (u32)events_.cap, d_ctl_);
+      kernel_launches++;
+      if (nu) {
+        k_match<<<(nu + 255) / 256, 256, 0, st_>>>(surv_.p, uniq_seq_.p, uniq_gap_.p, nu, trow_[cur_].p, nt_, using_x,
+                                                  best_match0, events_.p, (u32)events_.cap, d_ctl_);
+        kernel_launches++;
+      }
+      CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      d2h_bytes += sizeof(PassCtl);
     }
     const u32 ne = h_ctl_->n_events;
     if (ne) {
@@ -926,9 +1021,9 @@ class DeviceEngine : public Engine {
     }
   }
   void events_cap_check() {
-    /* worst case per pass is bounded by 3 events per survivor, but the window filter keeps the
-       real number tiny; start generous and abort loudly if ever exceeded */
-    events_.ensure(1u << 20);
+    /* the window filter keeps the real number tiny; on overflow run_pass grows the buffer and re-emits */
+    const char* cap_env = getenv("RIES_EVENTS_CAP"); /* test hook: start tiny to exercise the regrow path */
+    events_.ensure(cap_env ? (size_t)atoi(cap_env) : (size_t)(1u << 16));
   }
   void exclusive_scan(const u32* in, u32* out, u32 n, u32* total_out) {
     u32 nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
@@ -956,6 +1051,10 @@ class DeviceEngine : public Engine {
   RiesParams* d_P_ = 0;
   PassCtl* d_ctl_ = 0;
   PassCtl* h_ctl_ = 0;
+  SortCtl* d_sortctl_ = 0;
+  DevBuf<u64> rs_state_;
+  size_t rs_state_zeroed_ = 0;
+  u32 rs_epoch_ = 0;
   DevBuf<FormDesc> forms_;
   DevBuf<Node> nodes_;
   DevBuf<Row> done_, surv_;

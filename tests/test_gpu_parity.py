@@ -70,3 +70,24 @@ def test_gpu_stats_are_consistent(product_lib):
     assert st["kernel_launches"] > 0
     assert st["lhs_distinct"] <= st["lhs_expressions"] and st["rhs_distinct"] <= st["rhs_expressions"]
     assert st["sort_keys"] == st["lhs_expressions"] + st["rhs_expressions"]
+
+
+def test_gpu_candidate_buffer_regrow(product_lib):
+    """A pass that finds more candidates than the device buffer holds must grow it and re-emit, not drop any."""
+    import subprocess
+    env = dict(os.environ, HOME="/nonexistent", RIES_EVENTS_CAP="3")
+    exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
+    for name in ("t25063_l3_F3_x", "i143_l3"):
+        case = [c for c in golden_cases() if c["name"] == name][0]
+        r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+        assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(name)
+
+
+def test_gpu_node_arena_regrow(product_lib):
+    """Same for the prefix arena: start with a tiny arena (test hook) and let overflow-and-rerun grow it."""
+    import subprocess
+    env = dict(os.environ, HOME="/nonexistent", RIES_ARENA_CAP="4096")
+    exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
+    case = [c for c in golden_cases() if c["name"] == "t25063_l3_F3_x"][0]
+    r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+    assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(case["name"])
