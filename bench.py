@@ -33,8 +33,13 @@ BATCH_SEED = 20261019
 # algorithmic bytes per survivor through the sort (read once + write once of a
 # 32-byte row) and per merged row (read old+new, write merged); flop weights per exec'd symbol.
 ROW_BYTES = 32
+NODE_BYTES = 48
 SORT_BYTES_PER_KEY = 2 * ROW_BYTES
 MERGE_BYTES_PER_ROW = 2 * ROW_BYTES
+# fp64 flops per exec() of each symbol: (value, extra for d/dx), SURVEY.md section 8(d)
+FLOP_WEIGHTS = {"n": (1, 1), "s": (1, 2), "r": (1, 3), "q": (1, 2), "+": (7, 1), "-": (7, 1), "*": (1, 3), "/": (1, 5),
+                "l": (25, 1), "E": (20, 1), "S": (50, 3), "C": (50, 3), "T": (45, 4), "^": (60, 30), "v": (62, 32),
+                "L": (52, 8), "A": (45, 7)}
 
 
 def peaks():
@@ -235,15 +240,30 @@ def main():
         return 0
 
     hbm_peak, peak_kind = peaks()
-    # HBM-bound stages: [1] order+radix sort, [2] dedupe/match/merge
+    # ---- roofline of the dominant stage (device time from CUDA events on the engine's stream) ----
+    # algorithmic bytes: K1 streams every live prefix once out (48 B) and once in (48 B)
+    # and writes each complete expression once (32 B row + 2 B form); the sort reads and writes each 32 B row
+    # once; the merge reads old+new and writes merged (2 x 32 B per merged row) + one 32 B neighbour read.
+    k1_bytes = nodes * 2 * NODE_BYTES + sort_keys * (ROW_BYTES + 2)
     sort_bytes = sort_keys * SORT_BYTES_PER_KEY
-    merge_bytes = merge_rows * MERGE_BYTES_PER_ROW + merge_rows * ROW_BYTES  # merge + one neighbour-search read
+    merge_bytes = merge_rows * MERGE_BYTES_PER_ROW + merge_rows * ROW_BYTES
     stages = [
-        ("K2 order+radix sort (k_rs_hist/k_rs_scatter)", sort_bytes, dev_ms[1], dev_launches[1]),
+        ("K1 enumerate+evaluate (k_expand)", k1_bytes, dev_ms[0], dev_launches[0]),
+        ("K2 order+radix sort (k_rs_hist_all/k_rs_onesweep)", sort_bytes, dev_ms[1], dev_launches[1]),
         ("K2/K3 classify+match+merge (k_classify/k_match/k_merge_*)", merge_bytes, dev_ms[2], dev_launches[2]),
     ]
     dom = max(stages, key=lambda s: s[2])
     achieved = dom[1] / (dom[2] / 1e3) / 1e9 if dom[2] > 0 else 0.0
+    # K1's fp64 figure: exec() calls per symbol (counted on the device) x SURVEY 8(d) flop weights
+    flops = 0.0
+    execs = 0
+    for st in (s[1] for s in per_step):
+        for ch, c in st["exec_calls"].items():
+            w, wdx = FLOP_WEIGHTS.get(ch, (0, 0))
+            flops += c["rhs"] * w + c["lhs"] * (w + wdx)
+            execs += c["rhs"] + c["lhs"]
+    fp64_peak = ries_b200.fp64_peak_tflops()
+    fp64_ach = flops / (dev_ms[0] / 1e3) / 1e12 if dev_ms[0] > 0 else 0.0
     roofline = {
         "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
@@ -251,7 +271,12 @@ def main():
         "avg_launch_ms": dom[2] / dom[3] if dom[3] else None,
         "stage_ms_per_step": {"K1_enum_eval": dev_ms[0] / args.steps, "K2_sort": dev_ms[1] / args.steps,
                               "K2K3_dedupe_match_merge": dev_ms[2] / args.steps, "K4_refine": dev_ms[3] / args.steps},
-        "note": "K1 is the fp64/latency-bound stage (no HBM roofline); see DESIGN.md section 6",
+        "stage_hbm_frac": {s[0].split(" ")[0] + "_" + str(i): (s[1] / (s[2] / 1e3) / 1e9 / hbm_peak if s[2] > 0 else 0.0)
+                           for i, s in enumerate(stages)},
+        "k1_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": fp64_ach / fp64_peak if fp64_peak else None, "peak_kind": "measured DFMA microbenchmark",
+                    "exec_calls_per_step": execs / args.steps, "algorithmic_flop_per_step": flops / args.steps},
+        "note": "K1 does ~14 flop per exec() and ~10 integer tests per exec(): it is bound by latency/issue, not by the fp64 pipe or HBM (profiles/); both fractions are given so the distance to either roof is explicit",
     }
 
     line = {

@@ -45,8 +45,16 @@ typedef struct ries_run_stats {
   unsigned long long sort_keys;            /* complete expressions that went through the radix sort */
   unsigned long long merge_rows;           /* table rows written by the per-pass merges */
   unsigned long long expand_nodes;         /* live prefixes evaluated by K1 */
+  /* exec() calls per symbol (the reference's g_exec_calls, ries.c:8943, split by symbol): op_char[i] is
+     the symbol, counted separately for RHS passes (value only) and LHS passes (value + d/dx) */
+  char op_char[48];
+  unsigned long long op_count_rhs[48], op_count_lhs[48];
 } ries_run_stats;
 void ries_last_stats(ries_run_stats *out);
+
+/* Measured fp64 FMA throughput of the device (TFLOP/s, a short DFMA microbenchmark on the engine's
+ * stream): the denominator bench.py uses for K1's fp64 figure.  0 without a GPU. */
+double ries_fp64_peak_tflops(void);
 
 /* "sm_100a" when the CUDA engine is usable in this process, else a diagnostic string. */
 const char *ries_engine_name(void);

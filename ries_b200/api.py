@@ -25,6 +25,8 @@ class _Stats(ctypes.Structure):
         ("stage_ms", ctypes.c_double * 4), ("stage_launches", ctypes.c_ulonglong * 4),
         ("sort_keys", ctypes.c_ulonglong), ("merge_rows", ctypes.c_ulonglong),
         ("expand_nodes", ctypes.c_ulonglong),
+        ("op_char", ctypes.c_char * 48), ("op_count_rhs", ctypes.c_ulonglong * 48),
+        ("op_count_lhs", ctypes.c_ulonglong * 48),
     ]
 
 
@@ -44,6 +46,8 @@ def _load():
         lib.ries_main.restype = ctypes.c_int
         lib.ries_last_stats.argtypes = [ctypes.POINTER(_Stats)]
         lib.ries_last_stats.restype = None
+        lib.ries_fp64_peak_tflops.argtypes = []
+        lib.ries_fp64_peak_tflops.restype = ctypes.c_double
         lib.ries_engine_name.argtypes = []
         lib.ries_engine_name.restype = ctypes.c_char_p
         _lib = lib
@@ -79,8 +83,19 @@ def last_stats():
     out = {}
     for name, _ in _Stats._fields_:
         v = getattr(s, name)
-        out[name] = list(v) if hasattr(v, "__len__") else v
+        if name == "op_char":
+            out[name] = bytes(s.op_char)
+        else:
+            out[name] = list(v) if hasattr(v, "__len__") else v
+    chars = out.pop("op_char")
+    out["exec_calls"] = {chr(c): {"rhs": out["op_count_rhs"][i], "lhs": out["op_count_lhs"][i]}
+                         for i, c in enumerate(chars) if c and (out["op_count_rhs"][i] or out["op_count_lhs"][i])}
+    del out["op_count_rhs"], out["op_count_lhs"]
     return out
+
+
+def fp64_peak_tflops():
+    return _load().ries_fp64_peak_tflops()
 
 
 def engine_name():

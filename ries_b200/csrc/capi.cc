@@ -7,6 +7,7 @@
 namespace ries {
 Engine* make_device_engine();
 void device_engine_report(Engine* e, DeviceReport* r);
+double device_engine_dfma_peak(Engine* e);
 }  // namespace ries
 
 static ries_run_stats g_last;
@@ -43,6 +44,11 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
     g_last.sort_keys = r.sort_keys;
     g_last.merge_rows = r.merge_rows;
     g_last.expand_nodes = r.expand_nodes;
+    for (int i = 0; i < 48; i++) {
+      g_last.op_char[i] = (char)r.op_char[i];
+      g_last.op_count_rhs[i] = r.op_count[0][i];
+      g_last.op_count_lhs[i] = r.op_count[1][i];
+    }
   }
   g_last.lhs_expressions = st.lhs_gen; g_last.rhs_expressions = st.rhs_gen;
   g_last.lhs_dead_ends = st.lhs_prune; g_last.rhs_dead_ends = st.rhs_prune;
@@ -56,6 +62,15 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
 
 extern "C" void ries_last_stats(ries_run_stats* out) {
   if (out) *out = g_last;
+}
+
+extern "C" double ries_fp64_peak_tflops(void) {
+  try {
+    if (!g_engine) g_engine = ries::make_device_engine();
+    return ries::device_engine_dfma_peak(g_engine);
+  } catch (...) {
+    return 0.0;
+  }
 }
 
 extern "C" const char* ries_engine_name(void) {

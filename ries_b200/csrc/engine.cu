@@ -141,10 +141,14 @@ __device__ __forceinline__ void tile_lookback(volatile u64* state, u32 tile, u32
   live_excl = lsum; done_excl = dsum;
 }
 
-__global__ void __launch_bounds__(EXP_THREADS)
+#ifndef EXP_MIN_BLOCKS
+#define EXP_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(EXP_THREADS, EXP_MIN_BLOCKS)
 k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, Node* nodes,
          Row* done, uint16_t* done_form, u32 cap_nodes, u32 cap_done, PassCtl* ctl,
-         volatile u64* tile_state, Staged* staged_all, int using_x, int cplx) {
+         volatile u64* tile_state, Staged* staged_all, u64* opcnt, int using_x, int cplx) {
+  __shared__ u32 s_opcnt[RIES_MAX_SYMS];
   __shared__ RiesParams P;
   __shared__ Node s_par[EXP_PARENTS];
   __shared__ unsigned short s_item[EXP_MAX_ITEMS];
@@ -160,6 +164,7 @@ k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, 
     u32* dst = (u32*)&P;
     for (u32 i = threadIdx.x; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];
     if (threadIdx.x == 0) s_dead = 0;
+    if (threadIdx.x < RIES_MAX_SYMS) s_opcnt[threadIdx.x] = 0;
   }
   __syncthreads();
   const u32 lvl_begin = ctl->lvl_begin, lvl_end = ctl->lvl_end;
@@ -227,6 +232,7 @@ k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, 
       const int cls = s_cls[pl];
       const int g = P.trial[cls][k];
       Node child;
+      atomicAdd(&s_opcnt[g], 1u); /* exec() calls per symbol: the algorithmic work of this kernel */
       int oc = expand_exec(P, cls, g, s_complete[pl] != 0, nodes, s_par[pl], p0 + pl, using_x, child);
       if (oc == OUT_DEAD) my_dead++;
       else if (oc == OUT_LIVE || oc == OUT_DONE) {
@@ -292,6 +298,18 @@ k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, 
   if (lane == 0 && my_dead) atomicAdd(&s_dead, my_dead);
   __syncthreads();
   if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
+  if (tid < RIES_MAX_SYMS && s_opcnt[tid]) atomicAdd(&opcnt[(using_x ? RIES_MAX_SYMS : 0) + tid], (u64)s_opcnt[tid]);
+}
+
+/* fp64 FMA peak of this device, measured (denominator for K1's fp64 figure): 8 independent chains/thread */
+__global__ void k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 /* After a level: advance the frontier, fold the level's totals, clear the tile states it used. */
@@ -757,6 +775,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
     CUDA_CHECK(cudaMalloc(&d_ctl_, sizeof(PassCtl)));
     CUDA_CHECK(cudaMalloc(&d_sortctl_, sizeof(SortCtl)));
+    CUDA_CHECK(cudaMalloc(&d_opcnt_, 2 * RIES_MAX_SYMS * sizeof(u64)));
     CUDA_CHECK(cudaMallocHost(&h_ctl_, sizeof(PassCtl)));
     const char* arena_env = getenv("RIES_ARENA_CAP"); /* test hook: start tiny to exercise overflow-and-rerun */
     const size_t arena0 = arena_env ? (size_t)atoi(arena_env) : (size_t)(1u << 20);
@@ -776,7 +795,9 @@ class DeviceEngine : public Engine {
 
   void begin(const RiesParams& P) override {
     CUDA_CHECK(cudaMemcpyAsync(d_P_, &P, sizeof(P), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaMemsetAsync(d_opcnt_, 0, 2 * RIES_MAX_SYMS * sizeof(u64), st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
+    memcpy(sym_chars_, P.sym_char, sizeof(sym_chars_));
     nt_ = 0;
     cur_ = 0;
     last_nu_ = 0;
@@ -822,7 +843,7 @@ class DeviceEngine : public Engine {
       for (int lvl = 0; lvl < max_len; lvl++) {
         k_expand<<<expand_grid_, EXP_THREADS, 0, st_>>>(d_P_, forms_.p, nodes_.p, done_.p, done_form_.p,
                                                        (u32)nodes_.cap, (u32)done_.cap, d_ctl_,
-                                                       (volatile u64*)tiles_.p, staged_.p, using_x, cplx);
+                                                       (volatile u64*)tiles_.p, staged_.p, d_opcnt_, using_x, cplx);
         k_level_finish<<<1, 1024, 0, st_>>>(d_ctl_, tiles_.p, (u32)nodes_.cap, (u32)done_.cap);
         kernel_launches += 2;
       }
@@ -977,6 +998,30 @@ class DeviceEngine : public Engine {
   unsigned long long merge_rows = 0;     /* rows written by the merges (old + new) */
   unsigned long long expand_nodes = 0;   /* live prefixes expanded (= exec'd prefixes) */
   u32 table_rows() const { return nt_; }
+  unsigned char sym_chars_[RIES_MAX_SYMS];
+  void read_opcounts(unsigned long long* out /* [2][RIES_MAX_SYMS] */) {
+    CUDA_CHECK(cudaMemcpy(out, d_opcnt_, 2 * RIES_MAX_SYMS * sizeof(u64), cudaMemcpyDeviceToHost));
+  }
+  double dfma_peak_tflops() {
+    const int blocks = num_sms_ * 8, threads = 512, iters = 1 << 14;
+    double* d = 0;
+    CUDA_CHECK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+      CUDA_CHECK(cudaEventRecord(a, st_));
+      k_dfma_peak<<<blocks, threads, 0, st_>>>(d, iters);
+      CUDA_CHECK(cudaEventRecord(b, st_));
+      CUDA_CHECK(cudaEventSynchronize(b));
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+      double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return best;
+  }
   void collect_stage_times() {
     for (size_t i = 0; i < pend_.size(); i++) {
       float ms = 0;
@@ -1052,6 +1097,7 @@ class DeviceEngine : public Engine {
   PassCtl* d_ctl_ = 0;
   PassCtl* h_ctl_ = 0;
   SortCtl* d_sortctl_ = 0;
+  u64* d_opcnt_ = 0;
   DevBuf<u64> rs_state_;
   size_t rs_state_zeroed_ = 0;
   u32 rs_epoch_ = 0;
@@ -1090,6 +1136,10 @@ void device_engine_report(Engine* e, DeviceReport* r) {
   r->merge_rows = d->merge_rows;
   r->expand_nodes = d->expand_nodes;
   r->table_rows = d->table_rows();
+  d->read_opcounts(&r->op_count[0][0]);
+  memcpy(r->op_char, d->sym_chars_, sizeof(r->op_char));
 }
+
+double device_engine_dfma_peak(Engine* e) { return static_cast<DeviceEngine*>(e)->dfma_peak_tflops(); }
 
 }  // namespace ries
