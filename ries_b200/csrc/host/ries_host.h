@@ -60,6 +60,7 @@ struct Options {
   bool NOS_options = false;
   bool allow_slow_message = true;
   bool no_cv_simplify = false;
+  bool solve_for_x = false; /* -s / --try-solve-for-x (ries.c:11756) */
   int out_format = OF_NORMAL;
   double max_matches = 100;
   double k_max_match_dist = -0.01;

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 
+#include "core/exec.h"
 #include "host/ries_host.h"
 
 namespace ries {
@@ -166,6 +167,165 @@ std::string pf_intfloat_wid(double x, int width) {
   return std::string(buf);
 }
 
+/* ---------------- infix formatting (-F1 / -F2) ---------------- */
+/* infix_preproc 6269, infix_1 5966-6240, infix_expand 6536: postfix -> one-character-per-symbol infix ->
+   names.  Phantom symbols (2900-2903): reversed subtract / divide / power. */
+namespace {
+const char PS_REVSUB = 1, PS_REVDIV = 2, PS_REVPOW = 4;
+
+struct InfixCtx {
+  const Setup* S;
+  bool explicit_multiply;
+  bool used_atan1, used_atan2;
+  char seft(unsigned char c) const {
+    if (c == (unsigned char)PS_REVSUB || c == (unsigned char)PS_REVDIV || c == 3 || c == (unsigned char)PS_REVPOW) return 'c';
+    int g = S->idx_of[c];
+    return g >= 0 ? S->info[g].seft : 0;
+  }
+};
+
+std::string infix_preproc(const InfixCtx& cx, const std::string& e) {
+  std::string o;
+  size_t n = e.size();
+  for (size_t i = 0; i < n; i++) {
+    char c = e[i];
+    char c1 = (i + 1 < n) ? e[i + 1] : 0, c2 = (i + 2 < n) ? e[i + 2] : 0;
+    if (c == '-' && c1 == 'n') { o.push_back(PS_REVSUB); i++; }
+    else if (c == '/' && c1 == 'r') { o.push_back(PS_REVDIV); i++; }
+    else if (c == ' ') { }
+    else if (c == 'n' && c1 && cx.seft((unsigned char)c1) == 'a' && c2 == '+') { o.push_back(c1); o.push_back(PS_REVSUB); i += 2; }
+    else if (c == 's') { o.push_back('2'); o.push_back('^'); }
+    else if (c == 'r') { o.push_back('1'); o.push_back(PS_REVDIV); }
+    else if (c == 'E') { o.push_back('e'); o.push_back(PS_REVPOW); }
+    else o.push_back(c);
+  }
+  return o;
+}
+
+bool in_set(const char* set, unsigned char c) { return c != 0 && strchr(set, (char)c) != 0; }
+
+/* Pulls one complete sub-expression off the END of `expr` (shortening it) and returns it as infix. */
+bool infix_1(InfixCtx& cx, std::string& expr, std::string& term, unsigned char& t_op) {
+  term.clear();
+  if (expr.empty()) return false;
+  unsigned char op = (unsigned char)expr.back();
+  expr.pop_back();
+  t_op = op;
+  switch (cx.seft(op)) {
+    case 'a':
+      term.push_back((char)op);
+      break;
+    case 'b': {
+      std::string a;
+      unsigned char op_a;
+      if (!infix_1(cx, expr, a, op_a)) return false;
+      bool swap = (op == 's');
+      bool paren_a = true;
+      if (op == 'n' && cx.seft(op_a) != 'c') paren_a = false;
+      if (!swap) term.push_back((char)op);
+      if (paren_a) term.push_back('(');
+      term += a;
+      if (paren_a) term.push_back(')');
+      if (swap) term.push_back((char)op);
+      break;
+    }
+    case 'c': {
+      std::string st_a, st_b;
+      unsigned char op_a, op_b;
+      if (!infix_1(cx, expr, st_b, op_b)) return false;
+      if (!infix_1(cx, expr, st_a, op_a)) return false;
+      bool swap = false;
+      if (op == '+' && cx.seft(op_a) == 'a' && op_a != 'x') swap = true;
+      if (op == '*') {
+        bool a_has_x = st_a.find('x') != std::string::npos;
+        bool b_has_x = st_b.find('x') != std::string::npos;
+        if (!a_has_x && op_b == 'x') {
+        } else if (cx.seft(op_a) != 'a' && cx.seft(op_b) == 'a') swap = true;
+        else if (op_a == 'x' && !b_has_x) swap = true;
+        if (cx.seft(op_a) == 'a' && op_b >= '0' && op_b <= '9') swap = true;
+        else if (op_a == 'x' && (op_b == 'e' || op_b == 'f' || op_b == 'p')) swap = true;
+      }
+      if (op == 'v') swap = true;
+      else if (op == 'L') swap = true;
+      if (op == (unsigned char)PS_REVSUB) { swap = true; op = '-'; t_op = '-'; }
+      else if (op == (unsigned char)PS_REVDIV) { swap = true; op = '/'; t_op = '/'; }
+      else if (op == (unsigned char)PS_REVPOW) { swap = true; op = '^'; t_op = '^'; }
+      const std::string* term_a = &st_a;
+      const std::string* term_b = &st_b;
+      if (swap) { term_a = &st_b; term_b = &st_a; unsigned char t = op_a; op_a = op_b; op_b = t; }
+      bool paren_a = false, paren_b = false, atan2_show_denom = true;
+      if (op == 'L') {
+        paren_b = true;
+        if (cx.seft(op_a) != 'a') paren_a = true;
+      } else if (op == 'A') {
+        if (op_b == '1') { atan2_show_denom = false; cx.used_atan1 = true; }
+        else cx.used_atan2 = true;
+      }
+      if (cx.seft(op_a) == 'c') {
+        paren_a = true;
+        if (in_set("+*/^vA", op_a) && in_set("+-", op)) paren_a = false;
+        else if (in_set("*^vA", op_a) && in_set("*/A", op)) paren_a = false;
+      }
+      if (cx.seft(op_b) == 'c') {
+        paren_b = true;
+        if (op == '+' && in_set("+-*/^vA", op_b)) paren_b = false;
+        else if (op == '-' && in_set("*/^vA", op_b)) paren_b = false;
+        else if (op == '*' && in_set("*/^vA", op_b)) paren_b = false;
+        else if (in_set("/A", op) && in_set("^vA", op_b)) paren_b = false;
+      }
+      if (in_set("LA", op)) term.push_back((char)op);
+      if (op == 'A') term.push_back('(');
+      if (paren_a) term.push_back('(');
+      term += *term_a;
+      if (paren_a) term.push_back(')');
+      char tb0 = term_b->empty() ? 0 : (*term_b)[0];
+      if (op == '*') {
+        if (cx.explicit_multiply) term.push_back((char)op);
+        else if (op_a <= '9' && paren_b) { }
+        else if (op_a <= '9' && tb0 <= '9') term.push_back((char)op);
+        else if (op_b == 'n') term.push_back((char)op);
+        else if (cx.seft(op_a) != 'a' || cx.seft(op_b) != 'a' || tb0 > '9') term.push_back('.');
+        else term.push_back((char)op);
+      } else if (op == 'A') {
+        if (atan2_show_denom) term.push_back(',');
+      } else if (op == 'L') {
+      } else {
+        term.push_back((char)op);
+      }
+      if (atan2_show_denom) {
+        if (paren_b) term.push_back('(');
+        term += *term_b;
+        if (paren_b) term.push_back(')');
+      }
+      if (op == 'A') term.push_back(')');
+      break;
+    }
+    default:
+      return false;
+  }
+  return true;
+}
+
+std::string infix_expand(const InfixCtx& cx, const std::string& in) {
+  std::string o;
+  for (size_t i = 0; i < in.size(); i++) {
+    unsigned char c = (unsigned char)in[i];
+    switch (c) {
+      case '(': o += "("; break;
+      case ',': o += ","; break;
+      case ')': o += ")"; break;
+      case '=': o += "="; break;
+      case '.': o += " "; break;
+      default: {
+        int g = cx.S->idx_of[c];
+        if (g >= 0 && cx.S->info[g].name_infix) o += cx.S->info[g].name_infix;
+      }
+    }
+  }
+  return o;
+}
+}  // namespace
+
 /* ---------------- the search ---------------- */
 
 namespace {
@@ -275,6 +435,7 @@ struct Search {
     if (exit_code) throw ExitRequest{exit_code};
   }
 
+  InfixCtx icx{0, false, false, false};
   /* legend bookkeeping: defsym_used ries.c:7417, describe_symbols 7434-7516 */
   bool def_needed[256] = {false};
   bool def_given[256] = {false};
@@ -283,9 +444,17 @@ struct Search {
       if (sym_defn((unsigned char)e[i], opt.out_format == OF_NORMAL)) def_needed[(unsigned char)e[i]] = true;
   }
   void describe_symbols() {
-    /* used_atan2 is only ever set by the infix formatter, so in postfix mode 'A' is never described */
-    def_needed[(unsigned char)'A'] = false;
+    /* used_atan1/used_atan2 are only ever set by the infix formatter (6128-6133), so in postfix mode 'A' is
+       never described; symbol 0 is the phantom "one-argument arctangent" (PHSYM_ATAN1, 3243) */
+    if (def_needed[(unsigned char)'A']) {
+      if (icx.used_atan1) def_needed[0] = true;
+      if (!icx.used_atan2) def_needed[(unsigned char)'A'] = false;
+    }
     bool normal = (opt.out_format == OF_NORMAL);
+    auto defn = [&](int sym) -> const char* {
+      if (sym == 0) return "atan2(s) = Angle of ray from origin through point (1,s)";
+      return sym_defn((unsigned char)sym, normal);
+    };
     const int kLineLeftInit = 79 - 2;
     int lineleft = kLineLeftInit;
     bool need_lf = true, going = true;
@@ -302,10 +471,10 @@ struct Search {
         int clen = 0, csym = 0;
         for (int sym = 0; sym < 256; sym++) {
           if (def_needed[sym] && !def_given[sym]) {
-            int sl = (int)strlen(sym_defn((unsigned char)sym, normal));
+            int sl = (int)strlen(defn(sym));
             if ((sl > clen) && (sl < lineleft)) {
               csym = sym;
-              candidate = sym_defn((unsigned char)sym, normal);
+              candidate = defn(sym);
               clen = sl;
             }
           }
@@ -347,12 +516,118 @@ struct Search {
     print_end(RIES_EXIT_NO_ERROR);
   }
 
-  /* report_match ries.c:7887 (postfix / FORTH formats; infix is a later row of the scope table) */
-  void report_match(const std::string& le, const std::string& re, double root, double delta) {
+  /* eval() ries.c:6777 on a symbol string of any length (only try_solve's sign test needs it): value at
+     x = target, 0 on any error exactly like the reference's default `*val = k_0`. */
+  double eval_string(const std::string& e) const {
+    const RiesParams& P = S.P;
+    Val stk[RIES_STK_MAX + 2];
+    int sp = 0;
+    bool has_x = e.find('x') != std::string::npos;
+    for (size_t i = 0; i < e.size(); i++) {
+      if ((int)i >= RIES_MAX_ELEN) return 0.0; /* ERR_EVAL_TOO_LONG */
+      int g = S.idx_of[(unsigned char)e[i]];
+      if (g < 0) return 0.0;
+      Val r;
+      int cls = P.sym_cls[g], err;
+      if (cls == 0) {
+        if (sp + 1 > RIES_STK_MAX) return 0.0;
+        err = exec_push(P, (unsigned char)e[i], P.target, r);
+        if (err) return 0.0;
+        stk[sp++] = r;
+      } else if (cls == 1) {
+        if (sp < 1) return 0.0;
+        err = exec_unary(P, (unsigned char)e[i], has_x, stk[sp - 1], r);
+        if (err) return 0.0;
+        stk[sp - 1] = r;
+      } else {
+        if (sp < 2) return 0.0;
+        err = exec_binary(P, (unsigned char)e[i], has_x, stk[sp - 2], stk[sp - 1], r);
+        if (err) return 0.0;
+        sp--;
+        stk[sp - 1] = r;
+      }
+    }
+    return sp > 0 ? stk[sp - 1].v : 0.0;
+  }
+
+  /* expr_break ries.c:6688 over endstack 6630: root operator and its argument(s) */
+  bool expr_break(const std::string& e, char* op, char* seft, std::string* a1, std::string* a2) const {
+    int sp = 0, last_sp_1 = -1;
+    a1->clear(); a2->clear();
+    if (e.empty()) return false;
+    for (size_t i = 0; i < e.size(); i++) {
+      int g = S.idx_of[(unsigned char)e[i]];
+      char sf = g >= 0 ? S.info[g].seft : 0;
+      if (sf == 'a') sp++;
+      else if (sf == 'c') sp--;
+      if (sp <= 0) return false;
+      if (sp == 1 && i + 1 < e.size()) last_sp_1 = (int)i;
+    }
+    if (sp > 1) return false;
+    int g = S.idx_of[(unsigned char)e.back()];
+    *op = e.back();
+    *seft = g >= 0 ? S.info[g].seft : 0;
+    if (*seft == 'b') *a1 = e.substr(0, e.size() - 1);
+    else if (*seft == 'c') {
+      *a1 = e.substr(0, (size_t)last_sp_1 + 1);
+      *a2 = e.substr((size_t)last_sp_1 + 1, e.size() - 1 - ((size_t)last_sp_1 + 1));
+    }
+    return true;
+  }
+
+  /* try_solve ries.c:6886-7123: peel the LHS's root operator onto the RHS until x (or a function with no
+     inverse here) is left.  Buffers are TS_ALLOC_L = 22 / TS_ALLOC_R = 88 symbols in the reference. */
+  void try_solve(std::string& lhs, std::string& rhs) const {
+    const size_t kR = 4 * RIES_EXPR_ALLOC - 1;
+    auto cat = [&](std::string& to, const std::string& add) {
+      for (size_t i = 0; i < add.size() && to.size() < kR; i++) to.push_back(add[i]);
+    };
+    bool going = true;
+    while (going) {
+      char op = 0, seft = 0;
+      std::string p1, p2;
+      if (!expr_break(lhs, &op, &seft, &p1, &p2)) break;
+      switch (op) {
+        case '+': cat(rhs, p2); cat(rhs, "-"); lhs = p1; break;
+        case '-': cat(rhs, p2); cat(rhs, "+"); lhs = p1; break;
+        case '*': cat(rhs, p2); cat(rhs, "/"); lhs = p1; break;
+        case '/': cat(rhs, p2); cat(rhs, "*"); lhs = p1; break;
+        case '^': cat(rhs, p2); cat(rhs, "v"); lhs = p1; break;
+        case 'L': { std::string t = p2; cat(t, rhs); cat(t, "^"); rhs = t; lhs = p1; break; }
+        case 'v': cat(rhs, p2); cat(rhs, "^"); lhs = p1; break;
+        case 'E': cat(rhs, "l"); lhs = p1; break;
+        case 'l': cat(rhs, "E"); lhs = p1; break;
+        case 'n': cat(rhs, "n"); lhs = p1; break;
+        case 'q': cat(rhs, "s"); lhs = p1; break;
+        case 'r': cat(rhs, "r"); lhs = p1; break;
+        case 's': {
+          cat(rhs, "q"); lhs = p1;
+          double l = eval_string(lhs), r = eval_string(rhs);
+          if (l * r < 0) cat(rhs, "n");
+          break;
+        }
+        default: going = false; break;
+      }
+    }
+  }
+
+  /* report_match ries.c:7887 */
+  void report_match(const std::string& le_in, const std::string& re_in, double root, double delta) {
     if ((delta == 0.0) && got_exact) return;
+    std::string le = le_in, re = re_in;
+    if (opt.solve_for_x) try_solve(le, re);
     std::string l_fmt, r_fmt;
     if (opt.out_format == OF_POSTFIX) {
       l_fmt = le; r_fmt = re;
+    } else if (opt.out_format == OF_CONDENSED || opt.out_format == OF_NORMAL) {
+      for (int side = 0; side < 2; side++) {
+        std::string pre = infix_preproc(icx, side ? re : le), term;
+        unsigned char top;
+        bool ok = infix_1(icx, pre, term, top);
+        if (!ok) term.clear();
+        else if (opt.out_format == OF_NORMAL) term = infix_expand(icx, term);
+        (side ? r_fmt : l_fmt) = term;
+      }
     } else {
       l_fmt = postfix_formatter(le); r_fmt = postfix_formatter(re);
     }
@@ -360,7 +635,7 @@ struct Search {
     int width = opt.relative_x ? 44 : 40;
     int equ_width = 5;
     int t_width = width + equ_width;
-    int l_pad = width / 2;
+    int l_pad = opt.solve_for_x ? width / 8 : width / 2;
     int r_pad = width - l_pad;
     l_pad -= lf_len; if (l_pad < 0) l_pad = 0;
     r_pad -= rf_len; if (r_pad < 0) r_pad = 0;
@@ -493,10 +768,7 @@ struct Search {
       return 0;
     }
     finish_setup(opt, S, out);
-    if (opt.out_format != OF_POSTFIX && opt.out_format != OF_FORTH) {
-      /* infix (-F1/-F2, the CLI default) is the first "next" row of the scope table */
-      opt.out_format = OF_FORTH;
-    }
+    icx.S = &S;
     best_match = S.init_match_dist;
 
     /* header ries.c:12327-12337 */

@@ -202,6 +202,10 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       o.restrict_exponents = TYPE_RAT;
     } else if (strcmp(a, "--rational-trig-args") == 0) {
       o.restrict_trig_args = TYPE_RAT;
+    } else if (strcmp(a, "--no-solve-for-x") == 0) {
+      o.solve_for_x = false;
+    } else if ((strncmp(a, "-s", 2) == 0) || (strcmp(a, "--try-solve-for-x") == 0)) {
+      o.solve_for_x = true;
     } else if ((strcmp(a, "--wide-output") == 0) || (strcmp(a, "--wide") == 0)) {
       o.wide_output = true;
       o.relative_x = true;

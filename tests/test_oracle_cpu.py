@@ -7,7 +7,9 @@ import pytest
 
 from conftest import ROOT, golden_cases, golden_text, run_binary
 
-SMALL = [c for c in golden_cases(big=False) if c["name"] not in ("t25063_l4_F3",)]
+SMALL = [c for c in golden_cases(big=False) if c["name"] not in ("t25063_l4_F3", "infix_l4")]
+# the C restatement covers the postfix/FORTH formats (-F0/-F3); infix is checked through the emulation + GPU
+POSTFIX = [c for c in SMALL if not c["name"].startswith(("infix_", "cfg1_", "solve_", "web_"))]
 
 
 @pytest.mark.parametrize("case", SMALL, ids=[c["name"] for c in SMALL])
@@ -18,7 +20,7 @@ def test_batch_emulation_matches_reference_goldens(oracle_build, case):
     assert got == golden_text(case["name"])
 
 
-@pytest.mark.parametrize("case", SMALL, ids=[c["name"] for c in SMALL])
+@pytest.mark.parametrize("case", POSTFIX, ids=[c["name"] for c in POSTFIX])
 def test_c_restatement_matches_reference_goldens(oracle_build, case):
     """oracle/ries_oracle.c (streaming restatement, stock libm) is pinned to the reference's outputs."""
     got = run_binary(os.path.join(oracle_build, "_build", "ries_oracle"), case["args"])
