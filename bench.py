@@ -120,6 +120,55 @@ def targets_for(n):
     return out
 
 
+def batch_workload(args, rank, local_rank, world, dist, torch, ries_b200):
+    """BASELINE config 5: targets ~ U(0,10) with 6 decimals (seed 20261019) at -l<level>, sharded round-robin
+    over ranks, `--workers` concurrent engines per GPU.  A step = the whole batch once."""
+    from ries_b200.parallel import shard_targets
+    level = args.level if args.level != DEFAULT_LEVEL else "4"
+    mine = shard_targets(targets_for(args.batch_size), rank, world)
+    flags = ["-l" + level, "-F3", "--no-slow-messages"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        ries_b200.batch(mine[:max(2 * args.workers, 8)], flags, workers=args.workers)
+    barrier()
+    t0 = time.perf_counter()
+    exprs = 0
+    for _ in range(args.steps):
+        for code, text in ries_b200.batch(mine, flags, workers=args.workers):
+            exprs += parse_expressions(text)
+    barrier()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([float(exprs), float(len(mine) * args.steps)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        tm = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        exprs_all, searches_all = t.tolist()
+        wall_all = tm.item()
+    else:
+        exprs_all, searches_all, wall_all = float(exprs), float(len(mine) * args.steps), wall
+    if rank == 0:
+        print(json.dumps({
+            "metric": "expressions_evaluated_per_sec", "value": exprs_all / wall_all, "unit": "expr/s",
+            "n_gpus": max(args.gpus, world), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall_all / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "batch of %d targets U(0,10) 6dp seed %d, ries <t> -l%s -F3, %d engines per GPU"
+                                   % (args.batch_size, BATCH_SEED, level, args.workers)},
+            "targets_per_sec": searches_all / wall_all,
+            "e2e": {"value": exprs_all / wall_all, "unit": "expr/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                    "api": "ries_batch(targets, flags, workers, done_cb) via ctypes"},
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -130,6 +179,10 @@ def main():
     ap.add_argument("--level", default=DEFAULT_LEVEL)
     ap.add_argument("--cpu-level", default="4", help="level of the bounded CPU sample (same target)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="search", choices=["search", "batch"],
+                    help="search: one full-depth search per step (default); batch: BASELINE config 5, many targets")
+    ap.add_argument("--batch-size", type=int, default=256, help="targets per step over all ranks (batch workload)")
+    ap.add_argument("--workers", type=int, default=8, help="concurrent engines per GPU (batch workload)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +230,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["RIES_DEVICE"] = str(local_rank)
     import ries_b200
+
+    if args.workload == "batch":
+        return batch_workload(args, rank, local_rank, world, dist, torch, ries_b200)
 
     if world > 1:
         target = targets_for(world)[rank]  # independent targets: BASELINE config-5 style sharding

@@ -52,6 +52,16 @@ typedef struct ries_run_stats {
 } ries_run_stats;
 void ries_last_stats(ries_run_stats *out);
 
+/* Many independent searches (BASELINE config 5: a batch of targets, each searched with the same flags).
+ * `flags` are the argv entries between the program name and the target, e.g. {"-l4", "-F3"}.  The searches
+ * run on `n_workers` host threads, each with its own device engine and CUDA stream on the same GPU, so the
+ * many small kernels of different searches overlap; results arrive through `done` (serialised, any order),
+ * `index` being the position in `targets`.  Returns the number of searches that ended with an error status
+ * other than 0 / -9998.  The reference has no batch mode: this is `for t in targets: ries <flags> t`. */
+typedef void (*ries_batch_done_fn)(void *ctx, int index, int exit_code, const char *text, size_t n);
+int ries_batch(int n_targets, const char *const *targets, int n_flags, const char *const *flags,
+               int n_workers, ries_batch_done_fn done, void *ctx);
+
 /* Measured fp64 FMA throughput of the device (TFLOP/s, a short DFMA microbenchmark on the engine's
  * stream): the denominator bench.py uses for K1's fp64 figure.  0 without a GPU. */
 double ries_fp64_peak_tflops(void);

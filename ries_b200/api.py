@@ -94,6 +94,29 @@ def last_stats():
     return out
 
 
+_BATCH_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_char),
+                             ctypes.c_size_t)
+
+
+def batch(targets, flags=("-F3",), workers=8):
+    """BASELINE config 5: many independent targets with the same flags.  Returns [(exit_code, text), ...] in
+    the order of `targets`.  `workers` host threads drive one device engine + CUDA stream each."""
+    lib = _load()
+    lib.ries_batch.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
+                               ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, _BATCH_FN, ctypes.c_void_p]
+    lib.ries_batch.restype = ctypes.c_int
+    t_arr = (ctypes.c_char_p * len(targets))(*[str(t).encode() for t in targets])
+    f_arr = (ctypes.c_char_p * max(len(flags), 1))(*[f.encode() for f in flags])
+    out = [None] * len(targets)
+
+    def _done(_ctx, index, code, buf, n):
+        out[index] = (code, ctypes.string_at(buf, n).decode("utf-8", "replace"))
+
+    cb = _BATCH_FN(_done)
+    lib.ries_batch(len(targets), t_arr, len(flags), f_arr, workers, cb, None)
+    return out
+
+
 def fp64_peak_tflops():
     return _load().ries_fp64_peak_tflops()
 

@@ -1,6 +1,12 @@
 // C ABI (include/ries_b200.h): main(argc, argv) of the reference (ries.c:12062) as a library call.
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
 #include "../../include/ries_b200.h"
 #include "host/ries_host.h"
 
@@ -80,4 +86,56 @@ extern "C" const char* ries_engine_name(void) {
   } catch (...) {
     return "unavailable: no CUDA device";
   }
+}
+
+/* ---- batch of independent targets ---- */
+namespace {
+void append_sink(void* ctx, const char* buf, size_t n) { static_cast<std::string*>(ctx)->append(buf, n); }
+}  // namespace
+
+extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags, const char* const* flags,
+                          int n_workers, ries_batch_done_fn done, void* ctx) {
+  if (n_targets <= 0) return 0;
+  if (n_workers < 1) n_workers = 1;
+  if (n_workers > n_targets) n_workers = n_targets;
+  std::atomic<int> next(0), failures(0);
+  std::mutex mu;
+  auto worker = [&]() {
+    ries::Engine* eng = 0;
+    try {
+      eng = ries::make_device_engine();
+    } catch (const ries::ExitRequest&) {
+      eng = 0;
+    }
+    while (true) {
+      int i = next.fetch_add(1);
+      if (i >= n_targets) break;
+      std::string text;
+      int code = 3;
+      if (eng) {
+        std::vector<std::string> args;
+        args.push_back("ries");
+        for (int k = 0; k < n_flags; k++) args.push_back(flags[k]);
+        args.push_back(targets[i]);
+        std::vector<char*> argv;
+        for (auto& a : args) argv.push_back(&a[0]);
+        ries::Sink sink{append_sink, &text};
+        ries::Options opt;
+        try {
+          ries::parse_args((int)argv.size(), argv.data(), opt, sink);
+          code = ries::run_search(opt, *eng, sink, 0);
+        } catch (const ries::ExitRequest& e) {
+          code = e.code;
+        }
+      }
+      if (code != 0 && code != RIES_EXIT_NO_ERROR) failures++;
+      std::lock_guard<std::mutex> lock(mu);
+      if (done) done(ctx, i, code, text.data(), text.size());
+    }
+    delete eng;
+  };
+  std::vector<std::thread> pool;
+  for (int w = 0; w < n_workers; w++) pool.emplace_back(worker);
+  for (auto& t : pool) t.join();
+  return failures.load();
 }

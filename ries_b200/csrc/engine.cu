@@ -176,7 +176,15 @@ k_expand(const RiesParams* __restrict__ gP, const FormDesc* __restrict__ forms, 
   Staged* staged = staged_all + (size_t)blockIdx.x * EXP_MAX_ITEMS;
   u32 my_dead = 0;
 
-  for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  /* Tiles are handed out by ticket, so a tile's predecessors (which its look-back waits on) are always
+     held by blocks that are already running: safe even when not every block of the grid is resident
+     (several engines sharing the GPU on different streams). */
+  __shared__ u32 s_tile;
+  while (true) {
+    if (tid == 0) s_tile = atomicAdd(&ctl->tile_ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= ntiles) break;
     const u32 p0 = lvl_begin + tile * EXP_PARENTS;
     /* ---- phase 1: integer tests, one thread per prefix ---- */
     u32 mask = 0;
@@ -335,6 +343,7 @@ __global__ void k_level_finish(PassCtl* ctl, u64* tile_state, u32 cap_nodes, u32
     if (new_nodes > cap_nodes) { ovf |= 1; }
     if (new_done > cap_done) { ovf |= 2; }
     ctl->overflow = ovf;
+    ctl->tile_ticket = 0;
     ctl->lvl_begin = old_end;
     /* on overflow stop expanding: the host grows the arenas and reruns the pass */
     ctl->lvl_end = (ovf & 3) ? old_end : (u32)new_nodes;

@@ -91,3 +91,24 @@ def test_gpu_node_arena_regrow(product_lib):
     case = [c for c in golden_cases() if c["name"] == "t25063_l3_F3_x"][0]
     r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
     assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(case["name"])
+
+
+def test_gpu_batch_of_targets_matches_reference(product_lib, oracle_build):
+    """BASELINE config 5 in miniature: a batch of seeded random targets searched concurrently (8 engines on
+    one GPU) must print, per target, exactly what the reference prints for that target alone."""
+    import ries_b200
+    ref = os.path.join(oracle_build, "_ref", "ries")
+    if not os.path.exists(ref):
+        ref = os.path.join(oracle_build, "_build", "ries_oracle")
+    rng = random.Random(20261019)
+    targets = ["%.6f" % rng.uniform(0, 10) for _ in range(24)]
+    flags = ["-l2", "-F3", "--no-slow-messages"]
+    got = ries_b200.batch(targets, flags, workers=8)
+    assert len(got) == len(targets) and all(g is not None for g in got)
+    for t, (code, text) in list(zip(targets, got))[::3]:
+        want = run_binary(ref, [t, "-l2", "-F3"])
+        shown = code & 0xff if code != 0 else 0
+        assert normalise(text) + "exit=%d\n" % shown == want, t
+    # and the same batch again gives the same bytes (engines are reused, streams interleave differently)
+    again = ries_b200.batch(targets, flags, workers=5)
+    assert [normalise(a[1]) for a in again] == [normalise(g[1]) for g in got]
