@@ -36,6 +36,7 @@ typedef struct ries_run_stats {
   int passes;
   int exit_code;
   double seconds;                           /* wall time inside ries_main */
+  double engine_seconds, forms_seconds;     /* of which: device passes (launch + wait), host form enumeration */
   unsigned long long kernel_launches;      /* CUDA kernels this call launched */
   unsigned long long h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host */
   /* device time per stage from CUDA events on the engine's stream, milliseconds, and the launches in

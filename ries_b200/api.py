@@ -20,7 +20,8 @@ class _Stats(ctypes.Structure):
         ("lhs_distinct", ctypes.c_longlong), ("rhs_distinct", ctypes.c_longlong),
         ("lhs_max_complexity", ctypes.c_int), ("rhs_max_complexity", ctypes.c_int),
         ("passes", ctypes.c_int), ("exit_code", ctypes.c_int),
-        ("seconds", ctypes.c_double), ("kernel_launches", ctypes.c_ulonglong),
+        ("seconds", ctypes.c_double), ("engine_seconds", ctypes.c_double), ("forms_seconds", ctypes.c_double),
+        ("kernel_launches", ctypes.c_ulonglong),
         ("h2d_bytes", ctypes.c_ulonglong), ("d2h_bytes", ctypes.c_ulonglong),
         ("stage_ms", ctypes.c_double * 4), ("stage_launches", ctypes.c_ulonglong * 4),
         ("sort_keys", ctypes.c_ulonglong), ("merge_rows", ctypes.c_ulonglong),

@@ -63,6 +63,8 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
   g_last.passes = st.passes;
   g_last.exit_code = code;
   g_last.seconds = st.exec_seconds;
+  g_last.engine_seconds = st.engine_seconds;
+  g_last.forms_seconds = st.forms_seconds;
   return code;
 }
 

@@ -125,6 +125,8 @@ struct RunStats {
   int lmax = 0, rmax = 0;
   int passes = 0;
   double exec_seconds = 0;
+  double engine_seconds = 0; /* inside Engine::run_pass (launch + wait) */
+  double forms_seconds = 0;  /* host form enumeration */
 };
 
 /* What the device engine measured during one search (CUDA events on its own stream). */

@@ -800,10 +800,14 @@ struct Search {
       if (st.lhs_insert > st.rhs_insert) { rmin++; rmax++; using_x = 0; cplx = rmax; }
       else { lmin++; lmax++; using_x = 1; cplx = lmax; }
       double genf = 0;
+      double tf0 = now_sec();
       gen_forms(S.P, cplx, cplx, forms, &genf);
       po = PassOutput();
       cur_ev = 0;
+      double tf1 = now_sec();
       eng.run_pass(using_x, cplx, forms, best_match, got_exact, po);
+      st.forms_seconds += tf1 - tf0;
+      st.engine_seconds += now_sec() - tf1;
       st.passes++;
       /* replay the pass's candidates in insertion order with the live threshold */
       for (size_t k = 0; k < po.events.size(); k++) {
