@@ -115,7 +115,7 @@ struct DevPtrs {
   double* tval[2];
   MatchEvent* events;
   u64* tiles;     /* K1 look-back state, one word per tile */
-  Staged* staged; /* K1 scratch, EXP_MAX_ITEMS per block */
+  Staged* staged; /* K1 scratch, 2 x EXP_MAX_ITEMS per block */
   u64* rs_state;  /* radix look-back state, 256 words per chunk */
   u64* cc_state;  /* classify look-back state, one word per chunk */
   SortCtl* sortctl;
@@ -176,17 +176,20 @@ __global__ void k_pass_end(PassCtl* C, TableState* T) {
 #define TS_DONE(x) ((u32)((x)&0x7fffffffull))
 #define TS_PACK(st, live, done) ((st) | ((u64)(live) << 31) | (u64)(done))
 
-/* Decoupled look-back over tile aggregates (two counters packed in one word). Called by warp 0. */
+/* Decoupled look-back over tile aggregates (two counters packed in one word), in two steps so that a
+   block can publish a tile's aggregate, go on to the next tile, and only then resolve the first one's
+   exclusive prefix (by then its predecessors have long published). */
+__device__ __forceinline__ void tile_publish(volatile u64* state, u32 tile, u32 live_agg, u32 done_agg) {
+  __threadfence();
+  state[tile] = TS_PACK(tile == 0 ? TS_INC : TS_AGG, live_agg, done_agg);
+}
+
+/* Called by warp 0. */
 __device__ __forceinline__ void tile_lookback(volatile u64* state, u32 tile, u32 live_agg, u32 done_agg,
                                               u32& live_excl, u32& done_excl) {
   const u32 lane = threadIdx.x & 31;
-  if (tile == 0) {
-    if (lane == 0) state[0] = TS_PACK(TS_INC, live_agg, done_agg);
-    live_excl = 0; done_excl = 0;
-    return;
-  }
-  if (lane == 0) state[tile] = TS_PACK(TS_AGG, live_agg, done_agg);
-  __threadfence();
+  live_excl = 0; done_excl = 0;
+  if (tile == 0) return;
   u32 lsum = 0, dsum = 0;
   int idx = (int)tile - 1;
   while (true) {
@@ -217,19 +220,28 @@ __device__ __forceinline__ void tile_lookback(volatile u64* state, u32 tile, u32
   live_excl = lsum; done_excl = dsum;
 }
 
+/* Shared-memory state of one tile between its front half (phases 1-3) and its back half (phase 4). */
+struct TileBuf {
+  Node par[EXP_PARENTS];
+  unsigned short item[EXP_MAX_ITEMS];
+  u32 live[EXP_PARENTS], done[EXP_PARENTS];   /* per prefix: bit per slot */
+  u32 lbase[EXP_PARENTS], dbase[EXP_PARENTS]; /* per prefix: exclusive child offsets inside the tile */
+  unsigned char cls[EXP_PARENTS], complete[EXP_PARENTS];
+  u32 total, tile, live_agg, done_agg;
+};
+
+#define EXP_DYN_SMEM (2 * sizeof(TileBuf))
+
 __global__ void __launch_bounds__(EXP_THREADS, EXP_MIN_BLOCKS)
 k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  TileBuf* s_buf = (TileBuf*)s_dyn; /* [2] */
   __shared__ u32 s_opcnt[RIES_MAX_SYMS];
   __shared__ RiesParams P;
-  __shared__ Node s_par[EXP_PARENTS];
-  __shared__ unsigned short s_item[EXP_MAX_ITEMS];
-  __shared__ u32 s_live[EXP_PARENTS], s_done[EXP_PARENTS];   /* per prefix: bit per slot */
-  __shared__ u32 s_lbase[EXP_PARENTS], s_dbase[EXP_PARENTS]; /* per prefix: exclusive child offsets */
-  __shared__ unsigned char s_cls[EXP_PARENTS], s_complete[EXP_PARENTS];
   __shared__ u32 s_wcnt[EXP_THREADS / 32][RIES_SLOTS];
   __shared__ u32 s_slot_base[RIES_SLOTS];
   __shared__ u32 s_wl[EXP_THREADS / 32], s_wd[EXP_THREADS / 32];
-  __shared__ u32 s_total, s_live_base, s_done_base, s_dead, s_tile, s_last;
+  __shared__ u32 s_live_base, s_done_base, s_dead, s_tile, s_last, s_next;
 
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lvl_begin = ctl->lvl_begin, lvl_end = ctl->lvl_end;
@@ -252,132 +264,164 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
     Node* nodes = D.nodes;
     const FormDesc* forms = D.forms;
     volatile u64* tile_state = (volatile u64*)D.tiles;
-    Staged* staged = D.staged + (size_t)blockIdx.x * EXP_MAX_ITEMS;
     u32 my_dead = 0;
+    int cur = 0;
+    bool have_prev = false;
 
     /* Tiles are handed out by ticket, so a tile's predecessors (which its look-back waits on) are always
        held by blocks that are already running: safe even when not every block of the grid is resident
-       (several engines sharing the GPU on different streams). */
+       (several engines sharing the GPU on different streams).  The loop is software-pipelined: the front
+       half of tile t+1 runs between the publication of tile t's aggregate and t's look-back. */
     while (true) {
-      if (tid == 0) s_tile = atomicAdd(&ctl->tile_ticket, 1u);
+      if (tid == 0) { s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next = 0; }
       __syncthreads();
       const u32 tile = s_tile;
-      if (tile >= ntiles) break;
-      const u32 p0 = lvl_begin + tile * EXP_PARENTS;
-      /* ---- phase 1: integer tests, one thread per prefix ---- */
-      u32 mask = 0;
-      {
-        const u32 p = p0 + tid;
-        if (p < lvl_end) {
-          const Node par = nodes[p];
-          s_par[tid] = par;
-          const FormDesc& F = forms[par.form];
-          const int cls = F.cls[par.len];
-          const int ns = P.cls_n[cls];
-          const int atts = prefix_attrs(P, F, par, using_x);
-          for (int k = 0; k < ns; k++) {
-            if (expand_tests(P, F, par, k, atts, using_x, cplx, cplx)) mask |= 1u << k;
-            else my_dead++;
+      const bool have_cur = tile < ntiles;
+      if (have_cur) {
+        TileBuf& B = s_buf[cur];
+        Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + cur) * EXP_MAX_ITEMS;
+        const u32 p0 = lvl_begin + tile * EXP_PARENTS;
+        /* ---- phase 1: integer tests, one thread per prefix ---- */
+        u32 mask = 0;
+        {
+          const u32 p = p0 + tid;
+          if (p < lvl_end) {
+            const Node par = nodes[p];
+            B.par[tid] = par;
+            const FormDesc& F = forms[par.form];
+            const int cls = F.cls[par.len];
+            const int ns = P.cls_n[cls];
+            const int atts = prefix_attrs(P, F, par, using_x);
+            for (int k = 0; k < ns; k++) {
+              if (expand_tests(P, F, par, k, atts, using_x, cplx, cplx)) mask |= 1u << k;
+              else my_dead++;
+            }
+            B.cls[tid] = (unsigned char)cls;
+            B.complete[tid] = (unsigned char)(par.len + 1 >= F.flen);
           }
-          s_cls[tid] = (unsigned char)cls;
-          s_complete[tid] = (unsigned char)(par.len + 1 >= F.flen);
+          B.live[tid] = 0;
+          B.done[tid] = 0;
         }
-        s_live[tid] = 0;
-        s_done[tid] = 0;
-      }
-      /* ---- phase 2: list the surviving pairs grouped by slot ---- */
+        /* ---- phase 2: list the surviving pairs grouped by slot ---- */
 #pragma unroll
-      for (int k = 0; k < RIES_SLOTS; k++) {
-        u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-        if (lane == 0) s_wcnt[warp][k] = __popc(b);
-      }
-      __syncthreads();
-      if (tid < RIES_SLOTS) { /* per slot: exclusive prefix over warps, and the slot's total */
-        u32 run = 0;
-        for (int w = 0; w < EXP_THREADS / 32; w++) { u32 c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
-        s_slot_base[tid] = run;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        u32 run = 0;
-        for (int k = 0; k < RIES_SLOTS; k++) { u32 c = s_slot_base[k]; s_slot_base[k] = run; run += c; }
-        s_total = run;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < RIES_SLOTS; k++) {
-        u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-        if ((mask >> k) & 1u) s_item[s_slot_base[k] + s_wcnt[warp][k] + __popc(b & lt)] = (unsigned short)((tid << 4) | k);
-      }
-      __syncthreads();
-      const u32 T = s_total;
-      /* ---- phase 3: exec + value prunes, one thread per listed pair ---- */
-      for (u32 i = tid; i < T; i += EXP_THREADS) {
-        const u32 it = s_item[i];
-        const u32 pl = it >> 4, k = it & 15u;
-        const int cls = s_cls[pl];
-        const int g = P.trial[cls][k];
-        Node child;
-        atomicAdd(&s_opcnt[g], 1u); /* exec() calls per symbol: the algorithmic work of this kernel */
-        int oc = expand_exec(P, cls, g, s_complete[pl] != 0, nodes, s_par[pl], p0 + pl, using_x, child);
-        if (oc == OUT_DEAD) my_dead++;
-        else if (oc == OUT_LIVE || oc == OUT_DONE) {
-          Staged st;
-          st.val = child.val; st.der = child.der; st.below = child.below; st.tag = child.tag; st.sp = child.sp;
-          st.pad0 = 0; st.pad1 = 0;
-          staged[i] = st;
-          if (oc == OUT_LIVE) { atomicOr(&s_live[pl], 1u << k); s_item[i] = (unsigned short)(it | IT_LIVE); }
-          else { atomicOr(&s_done[pl], 1u << k); s_item[i] = (unsigned short)(it | IT_DONE); }
+        for (int k = 0; k < RIES_SLOTS; k++) {
+          u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
+          if (lane == 0) s_wcnt[warp][k] = __popc(b);
         }
-      }
-      __syncthreads();
-      /* ---- phase 4: ordered append ---- */
-      {
-        u32 nl = __popc(s_live[tid]), nd = __popc(s_done[tid]);
-        u32 il = nl, id = nd;
-        for (int o = 1; o < 32; o <<= 1) {
-          u32 a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, id, o);
-          if (lane >= (u32)o) { il += a; id += b; }
-        }
-        if (lane == 31) { s_wl[warp] = il; s_wd[warp] = id; }
         __syncthreads();
-        u32 wl = 0, wd = 0;
-        for (u32 w = 0; w < warp; w++) { wl += s_wl[w]; wd += s_wd[w]; }
-        s_lbase[tid] = wl + il - nl;
-        s_dbase[tid] = wd + id - nd;
+        if (tid < RIES_SLOTS) { /* per slot: exclusive prefix over warps, and the slot's total */
+          u32 run = 0;
+          for (int w = 0; w < EXP_THREADS / 32; w++) { u32 c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+          s_slot_base[tid] = run;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          u32 run = 0;
+          for (int k = 0; k < RIES_SLOTS; k++) { u32 c = s_slot_base[k]; s_slot_base[k] = run; run += c; }
+          B.total = run;
+          B.tile = tile;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RIES_SLOTS; k++) {
+          u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
+          if ((mask >> k) & 1u) B.item[s_slot_base[k] + s_wcnt[warp][k] + __popc(b & lt)] = (unsigned short)((tid << 4) | k);
+        }
+        __syncthreads();
+        const u32 T = B.total;
+        /* ---- phase 3: exec + value prunes; warps pull 32 listed pairs at a time (a warp's batch is
+           almost always one operator, and heavy operators spread over the warps) ---- */
+        while (true) {
+          u32 b0 = 0;
+          if (lane == 0) b0 = atomicAdd(&s_next, 32u);
+          b0 = __shfl_sync(0xffffffffu, b0, 0);
+          if (b0 >= T) break;
+          const u32 i = b0 + lane;
+          if (i < T) {
+            const u32 it = B.item[i];
+            const u32 pl = it >> 4, k = it & 15u;
+            const int cls = B.cls[pl];
+            const int g = P.trial[cls][k];
+            Node child;
+            atomicAdd(&s_opcnt[g], 1u); /* exec() calls per symbol: the algorithmic work of this kernel */
+            int oc = expand_exec(P, cls, g, B.complete[pl] != 0, nodes, B.par[pl], p0 + pl, using_x, child);
+            if (oc == OUT_DEAD) my_dead++;
+            else if (oc == OUT_LIVE || oc == OUT_DONE) {
+              Staged st;
+              st.val = child.val; st.der = child.der; st.below = child.below; st.tag = child.tag; st.sp = child.sp;
+              st.pad0 = 0; st.pad1 = 0;
+              staged[i] = st;
+              if (oc == OUT_LIVE) { atomicOr(&B.live[pl], 1u << k); B.item[i] = (unsigned short)(it | IT_LIVE); }
+              else { atomicOr(&B.done[pl], 1u << k); B.item[i] = (unsigned short)(it | IT_DONE); }
+            }
+          }
+        }
+        __syncthreads();
+        /* child offsets inside the tile, and the tile's aggregate -> published at once */
+        {
+          u32 nl = __popc(B.live[tid]), nd = __popc(B.done[tid]);
+          u32 il = nl, id = nd;
+          for (int o = 1; o < 32; o <<= 1) {
+            u32 a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, id, o);
+            if (lane >= (u32)o) { il += a; id += b; }
+          }
+          if (lane == 31) { s_wl[warp] = il; s_wd[warp] = id; }
+          __syncthreads();
+          u32 wl = 0, wd = 0, la = 0, da = 0;
+          for (u32 w = 0; w < EXP_THREADS / 32; w++) {
+            const u32 a = s_wl[w], b = s_wd[w];
+            if (w < warp) { wl += a; wd += b; }
+            la += a; da += b;
+          }
+          B.lbase[tid] = wl + il - nl;
+          B.dbase[tid] = wd + id - nd;
+          if (tid == 0) {
+            B.live_agg = la; B.done_agg = da;
+            tile_publish(tile_state, tile, la, da);
+          }
+        }
+      }
+      /* ---- phase 4 of the PREVIOUS tile: ordered append ---- */
+      if (have_prev) {
+        TileBuf& B = s_buf[cur ^ 1];
+        const Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * EXP_MAX_ITEMS;
         if (warp == 0) {
-          u32 la = 0, da = 0;
-          for (int w = 0; w < EXP_THREADS / 32; w++) { la += s_wl[w]; da += s_wd[w]; }
           u32 le, de;
-          tile_lookback(tile_state, tile, la, da, le, de);
+          tile_lookback(tile_state, B.tile, B.live_agg, B.done_agg, le, de);
           if (lane == 0) { s_live_base = le; s_done_base = de; }
         }
         __syncthreads();
-      }
-      for (u32 i = tid; i < T; i += EXP_THREADS) {
-        const u32 it = s_item[i];
-        if (!(it & (IT_LIVE | IT_DONE))) continue;
-        const u32 pl = (it >> 4) & 255u, k = it & 15u;
-        const Node& par = s_par[pl];
-        const int g = P.trial[s_cls[pl]][k];
-        const Staged st = staged[i];
-        Node child;
-        child.val = st.val; child.der = st.der; child.below = st.below; child.tag = st.tag; child.sp = st.sp;
-        expand_finish(P, par, g, child);
-        const u32 below_k = (1u << k) - 1;
-        if (it & IT_LIVE) {
-          u32 pos = lvl_end + s_live_base + s_lbase[pl] + __popc(s_live[pl] & below_k);
-          if (pos < cap_nodes) nodes[pos] = child;
-        } else {
-          u32 pos = done_base0 + s_done_base + s_dbase[pl] + __popc(s_done[pl] & below_k);
-          if (pos < cap_done) {
-            Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
-            D.done[pos] = r;
-            D.done_form[pos] = child.form;
+        const u32 T = B.total;
+        const u32 p_tile = B.tile;
+        (void)p_tile;
+        for (u32 i = tid; i < T; i += EXP_THREADS) {
+          const u32 it = B.item[i];
+          if (!(it & (IT_LIVE | IT_DONE))) continue;
+          const u32 pl = (it >> 4) & 255u, k = it & 15u;
+          const Node& par = B.par[pl];
+          const int g = P.trial[B.cls[pl]][k];
+          const Staged st = staged[i];
+          Node child;
+          child.val = st.val; child.der = st.der; child.below = st.below; child.tag = st.tag; child.sp = st.sp;
+          expand_finish(P, par, g, child);
+          const u32 below_k = (1u << k) - 1;
+          if (it & IT_LIVE) {
+            u32 pos = lvl_end + s_live_base + B.lbase[pl] + __popc(B.live[pl] & below_k);
+            if (pos < cap_nodes) nodes[pos] = child;
+          } else {
+            u32 pos = done_base0 + s_done_base + B.dbase[pl] + __popc(B.done[pl] & below_k);
+            if (pos < cap_done) {
+              Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
+              D.done[pos] = r;
+              D.done_form[pos] = child.form;
+            }
           }
         }
       }
-      __syncthreads(); /* shared tile state is reused by the next tile */
+      __syncthreads(); /* s_tile, s_live_base and the buffers are reused by the next round */
+      if (!have_cur) break;
+      have_prev = true;
+      cur ^= 1;
     }
     /* block-level dead-end count -> one atomic per block */
     for (int o = 16; o > 0; o >>= 1) my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
@@ -910,7 +954,8 @@ class DeviceEngine : public Engine {
     }
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     int occ = 1;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, EXP_THREADS, 0));
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_DYN_SMEM));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, EXP_THREADS, EXP_DYN_SMEM));
     if (occ < 1) occ = 1;
     expand_grid_ = (u32)(num_sms_ * occ);
     wide_grid_ = (u32)(num_sms_ * 8);
@@ -931,7 +976,7 @@ class DeviceEngine : public Engine {
     const char* arena_env = getenv("RIES_ARENA_CAP"); /* test hook: start tiny to exercise overflow-and-rerun */
     const size_t arena0 = arena_env ? (size_t)atoi(arena_env) : (size_t)(1u << 20);
     const char* cap_env = getenv("RIES_EVENTS_CAP"); /* test hook: start tiny to exercise the regrow path */
-    staged_.ensure((size_t)expand_grid_ * EXP_MAX_ITEMS, st_);
+    staged_.ensure((size_t)expand_grid_ * 2 * EXP_MAX_ITEMS, st_);
     events_.ensure(std::max<size_t>(cap_env ? (size_t)atoi(cap_env) : (size_t)(1u << 14), 1), st_);
     forms_.ensure(4096, st_);
     for (int i = 0; i < 3; i++) form_[i].ensure(4096, st_);
@@ -1129,7 +1174,7 @@ class DeviceEngine : public Engine {
     switch (stage) {
       case 0:
         k_pass_begin<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-        for (int lvl = 0; lvl < max_len; lvl++) k_expand<<<g_exp, EXP_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
+        for (int lvl = 0; lvl < max_len; lvl++) k_expand<<<g_exp, EXP_THREADS, EXP_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_);
         break;
       case 1:
         k_form_bounds<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_);

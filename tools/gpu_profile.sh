@@ -1,0 +1,32 @@
+#!/bin/bash
+# Launch list + one `--set full` capture of the longest launch of each heavy kernel, for one search.
+# usage (on the GPU box): tools/gpu_profile.sh <tag> <ries args...>      outputs under gpurun_out/
+set -u
+tag=$1; shift
+out=gpurun_out
+mkdir -p $out
+export RIES_NO_GRAPHS=1   # same kernels, launched directly, so that every launch is one ncu record
+./ries_b200/bin/ries "$@" > $out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -5 $out/${tag}_plain.log; exit 1; }
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches.csv \
+  ./ries_b200/bin/ries "$@" > $out/${tag}_ncu1.log 2>&1
+python tools/ncu_summary.py $out/${tag}_launches.csv | tee $out/${tag}_launch_summary.txt
+python - "$out/${tag}_launches.csv" > $out/${tag}_pick.txt <<'PY'
+import csv, sys
+lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
+best = {}
+for i, row in enumerate(csv.DictReader(lines)):
+    name = row["Kernel Name"].split("(")[0]
+    v = float(row["Metric Value"].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(row["Metric Unit"], 1)
+    if name not in best or v > best[name][1]:
+        best[name] = (int(row["ID"]), v)
+import os
+for name in os.environ.get("KERNELS", "k_expand k_rs_onesweep k_classify_compact k_merge_old k_reorder k_match k_merge_new k_rs_hist_all").split():
+    if name in best:
+        print(name, best[name][0])
+PY
+cat $out/${tag}_pick.txt
+while read name idx; do
+  timeout 600 ncu --set full --import-source on --clock-control none -s $idx -c 1 -f -o $out/${tag}_${name} \
+    ./ries_b200/bin/ries "$@" > $out/${tag}_ncu_${name}.log 2>&1
+  ls -la $out/${tag}_${name}.ncu-rep
+done < $out/${tag}_pick.txt
