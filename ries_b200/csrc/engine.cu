@@ -717,25 +717,58 @@ __device__ __forceinline__ void push_event(MatchEvent* events, u32 cap, PassCtl*
   }
 }
 
+/* Inverse of key_of. */
+__device__ __forceinline__ double val_of_key(u64 k) {
+  u64 b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+/* Lower bound by a whole warp: 32 probes per step split the range in 33, so a 3e7-row table takes five
+   dependent loads instead of twenty-five. */
+__device__ __forceinline__ u32 warp_lower_bound(const double* __restrict__ a, u32 n, double v) {
+  const u32 lane = threadIdx.x & 31;
+  u32 lo = 0, hi = n; /* the answer is in [lo, hi] */
+  while (hi - lo > 32) {
+    const u32 step = (hi - lo + 32) / 33;
+    const u32 q = lo + (lane + 1) * step - 1;
+    const bool lt = (q < hi) && (a[q] < v);
+    const u32 c = __popc(__ballot_sync(0xffffffffu, lt));
+    const u32 nhi = lo + (c + 1) * step - 1;
+    lo += c * step;
+    if (c < 32 && nhi < hi) hi = nhi; /* probe c exists, is in range and is >= v */
+  }
+  const bool lt = (lo + lane < hi) && (a[lo + lane] < v);
+  return lo + __popc(__ballot_sync(0xffffffffu, lt));
+}
+
 /* For every survivor in sorted order: is it a new distinct value?  New rows are compacted (ticketed
    chunks + look-back keep them in value order) together with their gap = lower bound in the old
    table.  Duplicates of an opposite-side table row become EXACT events (check_exact_match's side
-   test, ries.c:8550-8593). */
+   test, ries.c:8550-8593).
+   The survivors of a chunk are consecutive in value order, so their lower bounds all fall between the
+   lower bounds of the chunk's first and last value: two warp searches find that window, the window of
+   table keys is staged in shared memory with coalesced loads, and the per-survivor searches run there.
+   Values come straight from the sorted keys (the key map is invertible): no gather from surv[]. */
 #define CC_THREADS 256
+#define CC_ITEMS 8
+#define CC_CHUNK (CC_THREADS * CC_ITEMS)
+#define CC_WIN 4096
 __global__ void __launch_bounds__(CC_THREADS)
 k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
-  __shared__ u32 s_warp[CC_THREADS / 32];
-  __shared__ u32 s_chunk, s_base;
+  __shared__ double s_win[CC_WIN + 1];
+  __shared__ u32 s_cnt[CC_ITEMS * (CC_THREADS / 32)];
+  __shared__ u32 s_chunk, s_base, s_lo, s_hi;
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
-  const u32 nchunks = (n + CC_THREADS - 1) / CC_THREADS;
+  const u32 nchunks = (n + CC_CHUNK - 1) / CC_CHUNK;
   if (blockIdx.x >= nchunks) return;
   const DevPtrs D = *Dp;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 cur = T->cur, nt = T->nt;
   const double* __restrict__ tval = D.tval[cur];
   const Row* __restrict__ trow = D.trow[cur];
-  const u32* __restrict__ idx = D.idx[0]; /* 8 digit passes: the sorted order ends in buffer 0 */
+  const u64* __restrict__ keys = D.keys[0]; /* 8 digit passes: the sorted order ends in buffer 0 */
+  const u32* __restrict__ idx = D.idx[0];
   const Row* __restrict__ surv = D.surv;
   const int using_x = A->using_x, skip_exact = A->skip_exact;
   volatile u64* state = (volatile u64*)D.cc_state;
@@ -745,60 +778,110 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
     __syncthreads();
     const u32 chunk = s_chunk;
     if (chunk >= nchunks) break;
-    const u32 i = chunk * CC_THREADS + tid;
-    u32 fl = 0, pos = 0, s = 0;
-    if (i < n) {
-      s = idx[i];
-      const double v = surv[s].val;
-      const bool dup_prev = (i > 0) && (surv[idx[i - 1]].val == v);
-      pos = lower_bound_val(tval, nt, v);
-      const bool in_table = (pos < nt) && (tval[pos] == v);
-      if (in_table) {
-        if (!skip_exact) {
-          Row t = trow[pos];
-          bool tree_is_lhs = (t.der != 0.0);
-          if (using_x ? !tree_is_lhs : tree_is_lhs) {
-            Row f = surv[s];
-            if (using_x) push_event(D.events, A->cap_events, C, s, EV_EXACT, f, t);
-            else push_event(D.events, A->cap_events, C, s, EV_EXACT, t, f);
+    const u32 base = chunk * CC_CHUNK;
+    const u32 last = min(base + CC_CHUNK, n) - 1;
+    /* window of the table that can hold this chunk's lower bounds */
+    if (warp == 0) {
+      u32 r = warp_lower_bound(tval, nt, val_of_key(keys[base]));
+      if (lane == 0) s_lo = r;
+    } else if (warp == 1) {
+      u32 r = warp_lower_bound(tval, nt, val_of_key(keys[last]));
+      if (lane == 0) s_hi = r;
+    }
+    __syncthreads();
+    const u32 lo = s_lo, hi = s_hi;        /* every lower bound of the chunk is in [lo, hi] */
+    const u32 wn = hi - lo;                 /* keys that take part in the searches */
+    const u32 wload = min(hi + 1, nt) - lo; /* + the one at `hi`, for the equality test */
+    const bool in_smem = wn <= CC_WIN;
+    if (in_smem)
+      for (u32 j = tid; j < wload; j += CC_THREADS) s_win[j] = tval[lo + j];
+    __syncthreads();
+    const double* win = in_smem ? s_win : tval + lo;
+    u32 pos[CC_ITEMS], sq[CC_ITEMS];
+    u32 flags = 0;
+#pragma unroll
+    for (int r = 0; r < CC_ITEMS; r++) {
+      const u32 i = base + r * CC_THREADS + tid;
+      bool fl = false;
+      pos[r] = 0; sq[r] = 0;
+      if (i < n) {
+        const u64 k = keys[i];
+        const double v = val_of_key(k);
+        const u32 s = idx[i];
+        sq[r] = s;
+        const bool dup_prev = (i > 0) && (keys[i - 1] == k);
+        u32 a = 0, b = wn;
+        while (a < b) {
+          u32 mid = (a + b) >> 1;
+          if (win[mid] < v) a = mid + 1; else b = mid;
+        }
+        const u32 p = lo + a;
+        pos[r] = p;
+        const bool in_table = (p < nt) && (win[a] == v);
+        if (in_table) {
+          if (!skip_exact) {
+            Row t = trow[p];
+            bool tree_is_lhs = (t.der != 0.0);
+            if (using_x ? !tree_is_lhs : tree_is_lhs) {
+              Row f = surv[s];
+              if (using_x) push_event(D.events, A->cap_events, C, s, EV_EXACT, f, t);
+              else push_event(D.events, A->cap_events, C, s, EV_EXACT, t, f);
+            }
           }
+        } else if (!dup_prev) {
+          fl = true;
         }
-      } else if (!dup_prev) {
-        fl = 1;
       }
-    }
-    /* block exclusive scan of the flags */
-    const u32 b = __ballot_sync(0xffffffffu, fl);
-    if (lane == 0) s_warp[warp] = __popc(b);
-    __syncthreads();
-    u32 woff = 0, total = 0;
-    for (u32 w = 0; w < CC_THREADS / 32; w++) { u32 c = s_warp[w]; if (w < warp) woff += c; total += c; }
-    /* look-back (one word per chunk: tag | flag | count) */
-    if (tid == 0) {
-      const u64 tag = epoch << 34;
-      u32 ex = 0;
-      if (chunk == 0) {
-        state[0] = tag | (RS_FLAG_INC << 32) | total;
-      } else {
-        state[chunk] = tag | (RS_FLAG_AGG << 32) | total;
-        int c = (int)chunk - 1;
-        while (c >= 0) {
-          u64 w;
-          do { w = state[c]; } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
-          ex += (u32)w;
-          if (((w >> 32) & 3ull) == RS_FLAG_INC) break;
-          c--;
-        }
-        state[chunk] = tag | (RS_FLAG_INC << 32) | (u64)(ex + total);
-      }
-      s_base = ex;
-      if (chunk == nchunks - 1) C->n_uniq = ex + total;
+      const u32 b = __ballot_sync(0xffffffffu, fl);
+      if (lane == 0) s_cnt[r * (CC_THREADS / 32) + warp] = __popc(b);
+      if (fl) flags |= 1u << r;
     }
     __syncthreads();
-    if (fl) {
-      const u32 u = s_base + woff + __popc(b & ((1u << lane) - 1));
-      D.uniq_seq[u] = s;
-      D.uniq_gap[u] = pos;
+    /* exclusive scan of the 64 (row, warp) counts in row-major order = survivor order */
+    u32 total = 0;
+    if (warp == 0) {
+      const u32 c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+      u32 inc = c0 + c1;
+      for (int o = 1; o < 32; o <<= 1) {
+        u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += v;
+      }
+      s_cnt[2 * lane] = inc - c0 - c1;
+      s_cnt[2 * lane + 1] = inc - c1;
+      total = __shfl_sync(0xffffffffu, inc, 31);
+      /* look-back (one word per chunk: tag | flag | count) */
+      if (lane == 0) {
+        const u64 tag = epoch << 34;
+        u32 ex = 0;
+        if (chunk == 0) {
+          state[0] = tag | (RS_FLAG_INC << 32) | total;
+        } else {
+          state[chunk] = tag | (RS_FLAG_AGG << 32) | total;
+          int c = (int)chunk - 1;
+          while (c >= 0) {
+            u64 w;
+            do { w = state[c]; } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
+            ex += (u32)w;
+            if (((w >> 32) & 3ull) == RS_FLAG_INC) break;
+            c--;
+          }
+          state[chunk] = tag | (RS_FLAG_INC << 32) | (u64)(ex + total);
+        }
+        s_base = ex;
+        if (chunk == nchunks - 1) C->n_uniq = ex + total;
+      }
+    }
+    __syncthreads();
+    const u32 cbase = s_base;
+#pragma unroll
+    for (int r = 0; r < CC_ITEMS; r++) {
+      const bool fl = (flags >> r) & 1u;
+      const u32 b = __ballot_sync(0xffffffffu, fl);
+      if (fl) {
+        const u32 u = cbase + s_cnt[r * (CC_THREADS / 32) + warp] + __popc(b & ((1u << lane) - 1));
+        D.uniq_seq[u] = sq[r];
+        D.uniq_gap[u] = pos[r];
+      }
     }
     __syncthreads();
   }
@@ -859,7 +942,34 @@ __global__ void k_merge_new(const DevPtrs* Dp, const PassCtl* C, const TableStat
   }
 }
 
-__global__ void k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
+/* Upper bound by a whole warp over a sorted u32 array: #{u : a[u] <= key}. */
+__device__ __forceinline__ u32 warp_upper_bound_u32(const u32* __restrict__ a, u32 n, u32 key) {
+  const u32 lane = threadIdx.x & 31;
+  u32 lo = 0, hi = n;
+  while (hi - lo > 32) {
+    const u32 step = (hi - lo + 32) / 33;
+    const u32 q = lo + (lane + 1) * step - 1;
+    const bool le = (q < hi) && (a[q] <= key);
+    const u32 c = __popc(__ballot_sync(0xffffffffu, le));
+    const u32 nhi = lo + (c + 1) * step - 1;
+    lo += c * step;
+    if (c < 32 && nhi < hi) hi = nhi;
+  }
+  const bool le = (lo + lane < hi) && (a[lo + lane] <= key);
+  return lo + __popc(__ballot_sync(0xffffffffu, le));
+}
+
+/* Old rows move up by the number of new rows whose gap is at or below them.  A chunk of consecutive
+   old rows only needs the slice of the (sorted) gap list between the counts of its first and last row:
+   found by two warp searches, staged in shared memory, searched there. */
+#define MO_THREADS 256
+#define MO_ITEMS 8
+#define MO_CHUNK (MO_THREADS * MO_ITEMS)
+#define MO_WIN 4096
+__global__ void __launch_bounds__(MO_THREADS)
+k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
+  __shared__ u32 s_win[MO_WIN];
+  __shared__ u32 s_lo, s_hi;
   if (C->overflow) return;
   const u32 nu = C->n_uniq;
   if (nu == 0) return; /* nothing inserted: the live buffer stays as it is */
@@ -869,16 +979,44 @@ __global__ void k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableStat
   Row* mrow = D.trow[T->cur ^ 1];
   double* mval = D.tval[T->cur ^ 1];
   const u32* __restrict__ uniq_gap = D.uniq_gap;
-  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < nt; j += gridDim.x * blockDim.x) {
-    /* new rows below table row j = #{u : gap[u] <= j} */
-    u32 lo = 0, hi = nu;
-    while (lo < hi) {
-      u32 mid = (lo + hi) >> 1;
-      if (uniq_gap[mid] <= j) lo = mid + 1; else hi = mid;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  (void)lane;
+  const u32 nchunks = (nt + MO_CHUNK - 1) / MO_CHUNK;
+  for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const u32 base = chunk * MO_CHUNK;
+    const u32 last = min(base + MO_CHUNK, nt) - 1;
+    if (warp == 0) {
+      u32 r = warp_upper_bound_u32(uniq_gap, nu, base);
+      if (lane == 0) s_lo = r;
+    } else if (warp == 1) {
+      u32 r = warp_upper_bound_u32(uniq_gap, nu, last);
+      if (lane == 0) s_hi = r;
     }
-    Row r = trow[j];
-    mrow[j + lo] = r;
-    mval[j + lo] = r.val;
+    __syncthreads();
+    const u32 lo = s_lo, wn = s_hi - s_lo;
+    const bool in_smem = wn <= MO_WIN;
+    if (in_smem)
+      for (u32 j = tid; j < wn; j += MO_THREADS) s_win[j] = uniq_gap[lo + j];
+    __syncthreads();
+    const u32* win = in_smem ? s_win : uniq_gap + lo;
+#pragma unroll
+    for (int r = 0; r < MO_ITEMS; r++) {
+      const u32 j = base + r * MO_THREADS + tid;
+      if (j < nt) {
+        u32 a = 0, b = wn;
+        if (wn) {
+          while (a < b) {
+            u32 mid = (a + b) >> 1;
+            if (win[mid] <= j) a = mid + 1; else b = mid;
+          }
+        }
+        const Row row = trow[j];
+        const u32 dst = j + lo + a;
+        mrow[dst] = row;
+        mval[dst] = row.val;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1188,7 +1326,7 @@ class DeviceEngine : public Engine {
         k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_match<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
-        k_merge_old<<<small ? 48u : wide_grid_, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+        k_merge_old<<<small ? 48u : wide_grid_, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
         break;
       default:
         k_refine<<<small ? 8 : 64, 64, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
@@ -1252,7 +1390,7 @@ class DeviceEngine : public Engine {
     /* look-back state must start as zeros (stale bits must not look like a live epoch / status) */
     ch |= tiles_.ensure(nodes_.cap / EXP_PARENTS + 2, st_, false, true);
     ch |= rs_state_.ensure((done_.cap / RS_CHUNK + 2) * 256, st_, false, true);
-    ch |= cc_state_.ensure(done_.cap / CC_THREADS + 2, st_, false, true);
+    ch |= cc_state_.ensure(done_.cap / CC_CHUNK + 2, st_, false, true);
     if (ch) ptrs_dirty_ = true;
   }
   void ensure_table(size_t rows) {
