@@ -54,6 +54,7 @@ typedef unsigned int u32;
 #define OVF_NODES 1u
 #define OVF_DONE 2u
 #define OVF_EVENTS 4u
+#define OVF_SMALL 8u /* a pass predicted small was not: rerun it through the general kernels */
 
 struct SortCtl {
   u32 ghist[8][256];
@@ -86,6 +87,16 @@ struct PassCtl {
   u32 pad;
   u64 dead;               /* dead-ends of the pass */
 };
+
+#define HEAD_EVENTS 16 /* candidates copied back together with the counters (one copy, one sync per pass) */
+struct PassOut {
+  PassCtl ctl;
+  MatchEvent head[HEAD_EVENTS];
+};
+
+/* What the host sends per pass, in one copy: the scalars, then the forms. */
+#define PASSIN_FORMS_OFFSET 256
+#define PASSIN_MAX_FORMS 65536
 
 /* Survives passes. */
 struct TableState {
@@ -147,11 +158,18 @@ __global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, Ta
   }
 }
 
-__global__ void k_pass_end(PassCtl* C, TableState* T) {
+__global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   if (threadIdx.x == 0 && !C->overflow && C->n_uniq) {
     T->cur ^= 1u;
     T->nt += C->n_uniq;
   }
+  /* the first few candidates ride along with the counters (C is the head of a PassOut) */
+  u32 ne = C->n_events;
+  if (ne > A->cap_events) ne = A->cap_events;
+  if (ne > HEAD_EVENTS) ne = HEAD_EVENTS;
+  const u32* src = (const u32*)D->events;
+  u32* dst = (u32*)((PassOut*)C)->head;
+  for (u32 i = threadIdx.x; i < ne * (sizeof(MatchEvent) / 4); i += blockDim.x) dst[i] = src[i];
 }
 
 /* ---------------------------------------------------------------- K1: enumerate+evaluate - */
@@ -551,10 +569,12 @@ __global__ void k_reorder(const DevPtrs* Dp, const PassCtl* C) {
    2048-key chunk gets its per-digit output offsets by decoupled look-back over the chunks before it
    (chunks are taken in ticket order, so equal keys keep their input order = insertion order). */
 #define RS_THREADS 256
-#define RS_ITEMS 8
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_ITEMS 16
 #define RS_CHUNK (RS_THREADS * RS_ITEMS)
 #define RS_FLAG_AGG 1ull
 #define RS_FLAG_INC 2ull
+#define RS_DYN_SMEM (RS_CHUNK * (sizeof(u64) + sizeof(u32)))
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist_all(const DevPtrs* Dp, const PassCtl* C) {
@@ -584,17 +604,29 @@ k_rs_hist_all(const DevPtrs* Dp, const PassCtl* C) {
   }
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+/* One digit pass.  Per 4096-key chunk:
+     rank     each warp ranks its own 512 keys (warp-striped, 16 rounds of match_any against a private
+              histogram): no block barrier inside
+     offsets  per bin: prefix over the warps, exclusive scan over the bins, look-back over earlier chunks
+     exchange keys go to shared memory in their chunk-local sorted position, and are written out from
+              there so that neighbouring threads write neighbouring addresses of the same bin
+   The order inside a bin is (chunk, warp, round, lane) = input order, so the sort is stable. */
+__global__ void __launch_bounds__(RS_THREADS, 2)
 k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass) {
-  __shared__ u32 s_off[256];
-  __shared__ u32 s_scan[256];
-  __shared__ u32 s_wcnt[RS_THREADS / 32][256];
+  extern __shared__ __align__(16) unsigned char s_rs_dyn[];
+  u64* s_keys = (u64*)s_rs_dyn;
+  u32* s_pays = (u32*)(s_keys + RS_CHUNK);
+  __shared__ u32 s_whist[RS_WARPS][256];
+  __shared__ u32 s_binex[256]; /* chunk-local exclusive offset of a bin */
+  __shared__ u32 s_goff[256];  /* global offset of a bin's first key of this chunk, minus s_binex */
+  __shared__ u32 s_wtot[RS_WARPS];
   __shared__ u32 s_chunk;
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
   const u32 nchunks = (n + RS_CHUNK - 1) / RS_CHUNK;
   if (blockIdx.x >= nchunks) return;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = (1u << lane) - 1;
   const int shift = pass * 8;
   const int src = pass & 1;
   const u64* __restrict__ keys_in = Dp->keys[src];
@@ -604,48 +636,102 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
   SortCtl* ctl = Dp->sortctl;
   volatile u64* state = (volatile u64*)Dp->rs_state;
   const u64 epoch = (u64)(T->epoch + (u32)pass);
-  /* exclusive scan of the digit's global histogram (256 bins, Hillis-Steele in shared memory) */
-  const u32 mine = ctl->ghist[pass][tid];
-  s_scan[tid] = mine;
-  for (int w = 0; w < RS_THREADS / 32; w++) s_wcnt[w][tid] = 0;
-  __syncthreads();
-  for (u32 o = 1; o < 256; o <<= 1) {
-    u32 v = (tid >= o) ? s_scan[tid - o] : 0;
+  /* exclusive scan of the digit's global histogram: bin `tid` starts at gbase */
+  u32 gbase;
+  {
+    const u32 mine = ctl->ghist[pass][tid];
+    u32 inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (u32)o) inc += v;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
     __syncthreads();
-    s_scan[tid] += v;
+    u32 wbase = 0;
+    for (u32 w = 0; w < warp; w++) wbase += s_wtot[w];
+    gbase = wbase + inc - mine;
     __syncthreads();
   }
-  const u32 gbase = s_scan[tid] - mine;
 
   while (true) {
     if (tid == 0) s_chunk = atomicAdd(&ctl->ticket[pass], 1u);
-    s_off[tid] = 0;
+    for (u32 j = tid; j < RS_WARPS * 256; j += RS_THREADS) (&s_whist[0][0])[j] = 0;
     __syncthreads();
     const u32 chunk = s_chunk;
     if (chunk >= nchunks) break;
     const u32 base = chunk * RS_CHUNK;
-    /* local histogram of this chunk */
+    const u32 m = min(RS_CHUNK, n - base); /* keys in this chunk */
     u64 key[RS_ITEMS];
     u32 pay[RS_ITEMS];
+    u32 rk[RS_ITEMS]; /* rank of the key among its warp's keys of the same digit */
+    const u32 wbase_i = warp * (RS_ITEMS * 32) + lane;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
-      u32 i = base + r * RS_THREADS + tid;
-      bool valid = i < n;
-      key[r] = valid ? keys_in[i] : 0;
-      pay[r] = valid ? idx_in[i] : 0;
-      if (valid) atomicAdd(&s_off[(u32)(key[r] >> shift) & 255u], 1u);
+      const u32 li = wbase_i + r * 32;
+      const bool valid = li < m;
+      key[r] = valid ? keys_in[base + li] : 0;
+      pay[r] = valid ? idx_in[base + li] : 0;
+    }
+    u32* wh = s_whist[warp];
+    /* all the match_any's first (independent of each other), then the short dependent chain through
+       the warp's histogram: every peer reads the running count, the leader bumps it */
+    u32 peers[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+      const bool valid = (wbase_i + r * 32) < m;
+      const u32 d = (u32)(key[r] >> shift) & 255u;
+      peers[r] = __match_any_sync(0xffffffffu, valid ? d : (0x100u | lane));
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+      const bool valid = (wbase_i + r * 32) < m;
+      const u32 d = (u32)(key[r] >> shift) & 255u;
+      const u32 prev = valid ? wh[d] : 0;
+      __syncwarp();
+      if (valid && (peers[r] & lt) == 0) wh[d] = prev + __popc(peers[r]);
+      __syncwarp();
+      rk[r] = prev + __popc(peers[r] & lt);
     }
     __syncthreads();
-    const u32 local = s_off[tid];
+    /* bin `tid`: exclusive prefix over the warps; its count in the chunk */
+    u32 cnt = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) { u32 c = s_whist[w][tid]; s_whist[w][tid] = cnt; cnt += c; }
+    /* publish the chunk's count of this bin right away; the look-back comes after the exchange, when
+       the chunks before this one have had time to publish theirs */
+    volatile u64* st = state + (size_t)chunk * 256 + tid;
+    const u64 tag = epoch << 34;
+    *st = tag | ((chunk == 0 ? RS_FLAG_INC : RS_FLAG_AGG) << 32) | cnt;
+    /* exclusive scan over the bins */
+    u32 inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (u32)o) inc += v;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
+    __syncthreads();
+    u32 binex;
+    {
+      u32 wb = 0;
+      for (u32 w = 0; w < warp; w++) wb += s_wtot[w];
+      binex = wb + inc - cnt;
+      s_binex[tid] = binex;
+    }
+    __syncthreads();
+    /* exchange through shared memory */
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+      if ((wbase_i + r * 32) < m) {
+        const u32 d = (u32)(key[r] >> shift) & 255u;
+        const u32 lp = s_binex[d] + wh[d] + rk[r];
+        s_keys[lp] = key[r];
+        s_pays[lp] = pay[r];
+      }
+    }
     /* decoupled look-back for bin `tid` over the chunks before this one */
     {
-      volatile u64* st = state + (size_t)chunk * 256 + tid;
-      const u64 tag = epoch << 34;
       u32 ex = 0;
-      if (chunk == 0) {
-        *st = tag | (RS_FLAG_INC << 32) | local;
-      } else {
-        *st = tag | (RS_FLAG_AGG << 32) | local;
+      if (chunk != 0) {
         int c = (int)chunk - 1;
         while (c >= 0) {
           u64 w;
@@ -654,40 +740,17 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
           if (((w >> 32) & 3ull) == RS_FLAG_INC) break;
           c--;
         }
-        *st = tag | (RS_FLAG_INC << 32) | (u64)(ex + local);
+        *st = tag | (RS_FLAG_INC << 32) | (u64)(ex + cnt);
       }
-      __syncthreads();
-      s_off[tid] = gbase + ex;
+      s_goff[tid] = gbase + ex - binex;
     }
     __syncthreads();
-    /* stable scatter: rows of 256 keys in order; inside a row, rank by (warp, lane) */
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-      u32 i = base + r * RS_THREADS + tid;
-      bool valid = i < n;
-      u32 d = (u32)(key[r] >> shift) & 255u;
-      u32 vmask = __ballot_sync(0xffffffffu, valid);
-      u32 peers = 0, rank = 0;
-      bool leader = false;
-      if (valid) {
-        peers = __match_any_sync(vmask, d);
-        rank = __popc(peers & ((1u << lane) - 1));
-        leader = (rank == 0);
-        if (leader) s_wcnt[warp][d] = __popc(peers);
-      }
-      __syncthreads();
-      u32 dest = 0;
-      if (valid) {
-        dest = s_off[d] + rank;
-        for (u32 w = 0; w < warp; w++) dest += s_wcnt[w][d];
-      }
-      __syncthreads();
-      if (valid && leader) {
-        atomicAdd(&s_off[d], (u32)__popc(peers));
-        s_wcnt[warp][d] = 0;
-      }
-      if (valid) { keys_out[dest] = key[r]; idx_out[dest] = pay[r]; }
-      __syncthreads();
+#pragma unroll 4
+    for (u32 j = tid; j < m; j += RS_THREADS) {
+      const u64 k = s_keys[j];
+      const u32 dest = s_goff[(u32)(k >> shift) & 255u] + j;
+      keys_out[dest] = k;
+      idx_out[dest] = s_pays[j];
     }
   }
 }
@@ -942,6 +1005,240 @@ __global__ void k_merge_new(const DevPtrs* Dp, const PassCtl* C, const TableStat
   }
 }
 
+/* ------------------------------------------------ small passes: one block does it all ---- */
+/* A pass with at most SP_CAP complete expressions (most passes of a search: sizes grow ~1.3x per
+   complexity step from one expression up) is launch-latency bound in the general kernels, so its
+   regroup + sort + classify + match + merge-new chain runs in ONE block here, with the keys resident in
+   shared memory.  Same algorithm, same order of results.  Insertion order is recovered by a stable
+   sort on the form index (every form completes at exactly one level, levels are appended in order). */
+#define SP_THREADS 1024
+#define SP_WARPS (SP_THREADS / 32)
+#define SP_ITEMS 4
+#define SP_CAP (SP_THREADS * SP_ITEMS)
+#define SP_DYN_SMEM (SP_CAP * (sizeof(u64) + sizeof(u32)) + SP_WARPS * 256 * sizeof(u32))
+
+/* one stable 8-bit digit pass over m keys held in shared memory (in place) */
+__device__ __forceinline__ void small_sort_pass(u64* s_keys, u32* s_pays, u32* s_whist, u32* s_binex,
+                                                u32* s_wtot, u32 m, int shift) {
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = (1u << lane) - 1;
+  for (u32 j = tid; j < SP_WARPS * 256; j += SP_THREADS) s_whist[j] = 0;
+  u64 key[SP_ITEMS];
+  u32 pay[SP_ITEMS], rk[SP_ITEMS], peers[SP_ITEMS];
+  const u32 li0 = warp * (SP_ITEMS * 32) + lane;
+#pragma unroll
+  for (int r = 0; r < SP_ITEMS; r++) {
+    const u32 li = li0 + r * 32;
+    key[r] = li < m ? s_keys[li] : 0;
+    pay[r] = li < m ? s_pays[li] : 0;
+  }
+  __syncthreads();
+  u32* wh = s_whist + warp * 256;
+#pragma unroll
+  for (int r = 0; r < SP_ITEMS; r++) {
+    const bool valid = (li0 + r * 32) < m;
+    const u32 d = (u32)(key[r] >> shift) & 255u;
+    peers[r] = __match_any_sync(0xffffffffu, valid ? d : (0x100u | lane));
+  }
+#pragma unroll
+  for (int r = 0; r < SP_ITEMS; r++) {
+    const bool valid = (li0 + r * 32) < m;
+    const u32 d = (u32)(key[r] >> shift) & 255u;
+    const u32 prev = valid ? wh[d] : 0;
+    __syncwarp();
+    if (valid && (peers[r] & lt) == 0) wh[d] = prev + __popc(peers[r]);
+    __syncwarp();
+    rk[r] = prev + __popc(peers[r] & lt);
+  }
+  __syncthreads();
+  u32 cnt = 0, inc = 0;
+  if (tid < 256) {
+    for (int w = 0; w < SP_WARPS; w++) { u32 c = s_whist[w * 256 + tid]; s_whist[w * 256 + tid] = cnt; cnt += c; }
+    inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (u32)o) inc += v;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
+  }
+  __syncthreads();
+  if (tid < 256) {
+    u32 wb = 0;
+    for (u32 w = 0; w < warp; w++) wb += s_wtot[w];
+    s_binex[tid] = wb + inc - cnt;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SP_ITEMS; r++) {
+    if ((li0 + r * 32) < m) {
+      const u32 d = (u32)(key[r] >> shift) & 255u;
+      const u32 lp = s_binex[d] + wh[d] + rk[r];
+      s_keys[lp] = key[r];
+      s_pays[lp] = pay[r];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+  extern __shared__ __align__(16) unsigned char s_sp_dyn[];
+  u64* s_keys = (u64*)s_sp_dyn;
+  u32* s_pays = (u32*)(s_keys + SP_CAP);
+  u32* s_whist = s_pays + SP_CAP;      /* SP_WARPS x 256 while sorting ... */
+  u32* s_useq = s_whist;               /* ... then the new rows: sequence number and gap */
+  u32* s_ugap = s_whist + SP_CAP;
+  __shared__ u32 s_binex[256];
+  __shared__ u32 s_wtot[8];
+  __shared__ u32 s_cnt[SP_ITEMS * SP_WARPS];
+  __shared__ u32 s_nu;
+  if (!pass_ok(C)) return;
+  const u32 n = C->done_count;
+  if (n == 0) return;
+  if (n > SP_CAP) { /* the host's size prediction was wrong: it reruns the pass through the general kernels */
+    if (threadIdx.x == 0) atomicOr(&C->overflow, OVF_SMALL);
+    return;
+  }
+  const DevPtrs D = *Dp;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  /* insertion order: stable sort of the done[] indices by form */
+  for (u32 i = tid; i < n; i += SP_THREADS) { s_keys[i] = D.done_form[i]; s_pays[i] = i; }
+  __syncthreads();
+  small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 0);
+  if (A->nforms > 256) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 8);
+  for (u32 j = tid; j < n; j += SP_THREADS) {
+    const Row r = D.done[s_pays[j]];
+    D.surv[j] = r;
+    s_keys[j] = key_of(r.val);
+    s_pays[j] = j;
+  }
+  __syncthreads();
+  /* stable sort by value */
+  for (int pass = 0; pass < 8; pass++) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, pass * 8);
+  /* classify: new distinct values, EXACT events */
+  const u32 cur = T->cur, nt = T->nt;
+  const double* __restrict__ tval = D.tval[cur];
+  const Row* __restrict__ trow = D.trow[cur];
+  const int using_x = A->using_x, skip_exact = A->skip_exact;
+  u32 pos[SP_ITEMS], sq[SP_ITEMS], flags = 0;
+  {
+    /* the thread's SP_ITEMS lower bounds advance in lock step: SP_ITEMS independent loads per round */
+    double v[SP_ITEMS];
+    u32 lo[SP_ITEMS], hi[SP_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SP_ITEMS; r++) {
+      const u32 i = r * SP_THREADS + tid;
+      v[r] = (i < n) ? val_of_key(s_keys[i]) : 0.0;
+      lo[r] = 0;
+      hi[r] = (i < n) ? nt : 0;
+    }
+    for (u32 span = nt; span != 0; span >>= 1) {
+      double t[SP_ITEMS];
+#pragma unroll
+      for (int r = 0; r < SP_ITEMS; r++) t[r] = (lo[r] < hi[r]) ? tval[(lo[r] + hi[r]) >> 1] : 0.0;
+#pragma unroll
+      for (int r = 0; r < SP_ITEMS; r++) {
+        if (lo[r] < hi[r]) {
+          const u32 mid = (lo[r] + hi[r]) >> 1;
+          if (t[r] < v[r]) lo[r] = mid + 1; else hi[r] = mid;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SP_ITEMS; r++) pos[r] = lo[r];
+  }
+#pragma unroll
+  for (int r = 0; r < SP_ITEMS; r++) {
+    const u32 i = r * SP_THREADS + tid;
+    bool fl = false;
+    sq[r] = 0;
+    if (i < n) {
+      const u64 k = s_keys[i];
+      const double v = val_of_key(k);
+      const u32 sidx = s_pays[i];
+      sq[r] = sidx;
+      const bool dup_prev = (i > 0) && (s_keys[i - 1] == k);
+      const u32 p = pos[r];
+      const bool in_table = (p < nt) && (tval[p] == v);
+      if (in_table) {
+        if (!skip_exact) {
+          Row t = trow[p];
+          bool tree_is_lhs = (t.der != 0.0);
+          if (using_x ? !tree_is_lhs : tree_is_lhs) {
+            Row f = D.surv[sidx];
+            if (using_x) push_event(D.events, A->cap_events, C, sidx, EV_EXACT, f, t);
+            else push_event(D.events, A->cap_events, C, sidx, EV_EXACT, t, f);
+          }
+        }
+      } else if (!dup_prev) {
+        fl = true;
+      }
+    }
+    const u32 b = __ballot_sync(0xffffffffu, fl);
+    if (lane == 0) s_cnt[r * SP_WARPS + warp] = __popc(b);
+    if (fl) flags |= 1u << r;
+  }
+  __syncthreads(); /* also: every read of s_keys/s_pays/s_whist is done, s_useq/s_ugap may be written */
+  if (warp == 0) { /* exclusive scan of the SP_ITEMS*SP_WARPS = 128 counts, 4 per lane */
+    u32 c[4], t = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { c[q] = s_cnt[4 * lane + q]; t += c[q]; }
+    u32 inc = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (u32)o) inc += v;
+    }
+    u32 run = inc - t;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { s_cnt[4 * lane + q] = run; run += c[q]; }
+    if (lane == 31) { s_nu = inc; C->n_uniq = inc; }
+  }
+  __syncthreads();
+  const u32 nu = s_nu;
+#pragma unroll
+  for (int r = 0; r < SP_ITEMS; r++) {
+    const bool fl = (flags >> r) & 1u;
+    const u32 b = __ballot_sync(0xffffffffu, fl);
+    if (fl) {
+      const u32 u = s_cnt[r * SP_WARPS + warp] + __popc(b & ((1u << lane) - 1));
+      s_useq[u] = sq[r]; s_ugap[u] = pos[r];
+      D.uniq_seq[u] = sq[r]; D.uniq_gap[u] = pos[r];
+    }
+  }
+  __syncthreads();
+  /* match (K3) and merge of the new rows */
+  const double best_match0 = A->best_match0;
+  Row* mrow = D.trow[cur ^ 1];
+  double* mval = D.tval[cur ^ 1];
+  for (u32 u = tid; u < nu; u += SP_THREADS) {
+    const u32 sidx = s_useq[u], g = s_ugap[u];
+    const Row f = D.surv[sidx];
+    mrow[u + g] = f;
+    mval[u + g] = f.val;
+    bool test_prev = g > 0, test_next = g < nt;
+    if (test_prev) {
+      for (u32 j = u; j-- > 0 && s_ugap[j] == g;)
+        if (s_useq[j] < sidx) { test_prev = false; break; }
+    }
+    if (test_next) {
+      for (u32 j = u + 1; j < nu && s_ugap[j] == g; j++)
+        if (s_useq[j] < sidx) { test_next = false; break; }
+    }
+    for (int side = 0; side < 2; side++) {
+      if (side == 0 ? !test_prev : !test_next) continue;
+      const Row o = trow[side == 0 ? g - 1 : g];
+      bool other_is_lhs = (o.der != 0.0);
+      if (using_x ? other_is_lhs : !other_is_lhs) continue;
+      const Row& L = using_x ? f : o;
+      const Row& R = using_x ? o : f;
+      double total = L.der - R.der;
+      double score = fabs((R.val - L.val) / total);
+      if (score > best_match0) continue; /* NaN passes, as in the reference's test (8270) */
+      push_event(D.events, A->cap_events, C, sidx, side == 0 ? EV_PREV : EV_NEXT, L, R);
+    }
+  }
+}
+
 /* Upper bound by a whole warp over a sorted u32 array: #{u : a[u] <= key}. */
 __device__ __forceinline__ u32 warp_upper_bound_u32(const u32* __restrict__ a, u32 n, u32 key) {
   const u32 lane = threadIdx.x & 31;
@@ -1064,7 +1361,6 @@ struct DevBuf {
   void release(cudaStream_t st) { if (p) cudaFreeAsync(p, st); p = 0; cap = 0; }
 };
 
-#define HEAD_EVENTS 16 /* candidates copied back together with the counters (one sync per pass) */
 
 class DeviceEngine : public Engine {
  public:
@@ -1093,21 +1389,33 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     int occ = 1;
     CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_DYN_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_DYN_SMEM));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, EXP_THREADS, EXP_DYN_SMEM));
     if (occ < 1) occ = 1;
     expand_grid_ = (u32)(num_sms_ * occ);
     wide_grid_ = (u32)(num_sms_ * 8);
     use_graphs_ = getenv("RIES_NO_GRAPHS") == 0;
+    use_small_post_ = getenv("RIES_NO_SMALL_POST") == 0; /* test hook: every pass through the general kernels */
+    force_small_post_ = getenv("RIES_FORCE_SMALL_POST") != 0;
+    CUDA_CHECK(cudaFuncSetAttribute(k_small_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_DYN_SMEM));
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
-    CUDA_CHECK(cudaMalloc(&d_ctl_, sizeof(PassCtl)));
-    CUDA_CHECK(cudaMalloc(&d_args_, sizeof(PassArgs)));
+    CUDA_CHECK(cudaMalloc(&d_out_, sizeof(PassOut)));
+    CUDA_CHECK(cudaMemset(d_out_, 0, sizeof(PassOut)));
+    d_ctl_ = &d_out_->ctl;
+    const size_t passin_bytes = PASSIN_FORMS_OFFSET + (size_t)PASSIN_MAX_FORMS * sizeof(FormDesc);
+    CUDA_CHECK(cudaMalloc(&d_passin_, passin_bytes));
+    d_args_ = (PassArgs*)d_passin_;
+    d_forms_ = (FormDesc*)(d_passin_ + PASSIN_FORMS_OFFSET);
     CUDA_CHECK(cudaMalloc(&d_tab_, sizeof(TableState)));
     CUDA_CHECK(cudaMalloc(&d_ptrs_, sizeof(DevPtrs)));
     CUDA_CHECK(cudaMalloc(&d_sortctl_, sizeof(SortCtl)));
     CUDA_CHECK(cudaMalloc(&d_opcnt_, 2 * RIES_MAX_SYMS * sizeof(u64)));
-    CUDA_CHECK(cudaMallocHost(&h_ctl_, sizeof(PassCtl)));
-    CUDA_CHECK(cudaMallocHost(&h_args_, sizeof(PassArgs)));
-    CUDA_CHECK(cudaMallocHost(&h_head_, HEAD_EVENTS * sizeof(MatchEvent)));
+    CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(PassOut)));
+    h_ctl_ = &h_out_->ctl;
+    h_head_ = h_out_->head;
+    CUDA_CHECK(cudaMallocHost(&h_passin_, passin_bytes));
+    h_args_ = (PassArgs*)h_passin_;
+    h_forms_ = (FormDesc*)(h_passin_ + PASSIN_FORMS_OFFSET);
     CUDA_CHECK(cudaMallocHost(&h_ptrs_, sizeof(DevPtrs)));
     memset(h_ptrs_, 0, sizeof(DevPtrs));
     for (int i = 0; i < 5; i++) CUDA_CHECK(cudaEventCreate(&ev_[i]));
@@ -1116,7 +1424,6 @@ class DeviceEngine : public Engine {
     const char* cap_env = getenv("RIES_EVENTS_CAP"); /* test hook: start tiny to exercise the regrow path */
     staged_.ensure((size_t)expand_grid_ * 2 * EXP_MAX_ITEMS, st_);
     events_.ensure(std::max<size_t>(cap_env ? (size_t)atoi(cap_env) : (size_t)(1u << 14), 1), st_);
-    forms_.ensure(4096, st_);
     for (int i = 0; i < 3; i++) form_[i].ensure(4096, st_);
     grow_arena(arena0, arena0);
     ensure_table(1u << 16);
@@ -1125,17 +1432,16 @@ class DeviceEngine : public Engine {
   ~DeviceEngine() override {
     cudaStreamSynchronize(st_);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
-    forms_.release(st_); nodes_.release(st_); done_.release(st_); done_form_.release(st_); surv_.release(st_);
+    nodes_.release(st_); done_.release(st_); done_form_.release(st_); surv_.release(st_);
     for (int b = 0; b < 2; b++) { keys_[b].release(st_); idx_[b].release(st_); trow_[b].release(st_); tval_[b].release(st_); }
     for (int i = 0; i < 3; i++) form_[i].release(st_);
     uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); tiles_.release(st_); staged_.release(st_);
     rs_state_.release(st_); cc_state_.release(st_);
     cudaStreamSynchronize(st_);
-    cudaFree(d_P_); cudaFree(d_ctl_); cudaFree(d_args_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
+    cudaFree(d_P_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
     cudaFree(d_opcnt_);
-    cudaFreeHost(h_ctl_); cudaFreeHost(h_args_); cudaFreeHost(h_head_); cudaFreeHost(h_ptrs_);
+    cudaFreeHost(h_out_); cudaFreeHost(h_passin_); cudaFreeHost(h_ptrs_);
     if (h_events_) cudaFreeHost(h_events_);
-    if (h_forms_) cudaFreeHost(h_forms_);
     for (int i = 0; i < 5; i++) cudaEventDestroy(ev_[i]);
     cudaStreamDestroy(st_);
   }
@@ -1175,26 +1481,19 @@ class DeviceEngine : public Engine {
     last_nu_ = 0;
     const u32 nforms = (u32)forms.size();
     if (nforms == 0) return;
-    if (nforms > 65535) {
+    if (nforms > PASSIN_MAX_FORMS - 1) {
       fprintf(stderr, "ries_b200: %u forms in one pass exceeds the 16-bit form index\n", nforms);
       abort();
     }
     int max_len = 0;
     for (const FormDesc& f : forms) max_len = std::max(max_len, (int)f.flen);
-    if (forms_.ensure(nforms, st_)) ptrs_dirty_ = true;
     for (int i = 0; i < 3; i++)
       if (form_[i].ensure(nforms, st_)) ptrs_dirty_ = true;
     if (nodes_.cap < (size_t)nforms + 16) grow_arena(nforms + 16, done_.cap);
-    /* forms: staged through a pinned buffer so the copy is truly asynchronous */
-    if (h_forms_cap_ < nforms) {
-      CUDA_CHECK(cudaStreamSynchronize(st_));
-      if (h_forms_) cudaFreeHost(h_forms_);
-      h_forms_cap_ = std::max<size_t>(nforms, h_forms_cap_ * 2);
-      CUDA_CHECK(cudaMallocHost(&h_forms_, h_forms_cap_ * sizeof(FormDesc)));
-    }
-    memcpy(h_forms_, forms.data(), nforms * sizeof(FormDesc));
+    memcpy(h_forms_, forms.data(), nforms * sizeof(FormDesc)); /* pinned; the last pass's copy has completed */
     h2d_bytes += nforms * sizeof(FormDesc) + sizeof(PassArgs);
 
+    bool no_small_post = !use_small_post_;
     while (true) {
       /* the merged table needs room for every survivor the arena can hold */
       ensure_table((size_t)nt_ + done_.cap);
@@ -1204,17 +1503,17 @@ class DeviceEngine : public Engine {
       h_args_->cap_nodes = (u32)std::min<size_t>(nodes_.cap, 0xffffffffu);
       h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
       h_args_->cap_events = (u32)events_.cap; h_args_->pad = 0;
-      CUDA_CHECK(cudaMemcpyAsync(forms_.p, h_forms_, nforms * sizeof(FormDesc), cudaMemcpyHostToDevice, st_));
-      CUDA_CHECK(cudaMemcpyAsync(d_args_, h_args_, sizeof(PassArgs), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
+                                 cudaMemcpyHostToDevice, st_));
       /* size class from the previous pass of the same side (sizes grow ~1.3-1.6x per complexity step) */
-      const int small = (prev_nodes_[using_x ? 1 : 0] <= 12000 && prev_done_[using_x ? 1 : 0] <= 3000) ? 1 : 0;
+      int small = (prev_nodes_[using_x ? 1 : 0] <= 12000 && prev_done_[using_x ? 1 : 0] <= 3000) ? 1 : 0;
+      if (small && !no_small_post && prev_done_[using_x ? 1 : 0] <= SP_CAP / 3 && nt_ <= 200000u) small = 2;
+      if (force_small_post_ && !no_small_post) small = 2; /* test hook: mispredict, to exercise the rerun */
       launch_pass(max_len, small);
-      CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
-      CUDA_CHECK(cudaMemcpyAsync(h_head_, events_.p, std::min<size_t>(HEAD_EVENTS, events_.cap) * sizeof(MatchEvent),
-                                 cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
       CUDA_CHECK(cudaStreamSynchronize(st_));
       CUDA_CHECK(cudaGetLastError());
-      d2h_bytes += sizeof(PassCtl) + HEAD_EVENTS * sizeof(MatchEvent);
+      d2h_bytes += sizeof(PassOut);
       collect_pass_times();
       const u32 ovf = h_ctl_->overflow;
       if (!ovf) break;
@@ -1226,6 +1525,7 @@ class DeviceEngine : public Engine {
       if (ovf & OVF_EVENTS) {
         if (events_.ensure((size_t)h_ctl_->n_events + 1024, st_)) ptrs_dirty_ = true;
       }
+      if (ovf & OVF_SMALL) no_small_post = true;
     }
     const u32 n = h_ctl_->done_count, nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
     prev_nodes_[using_x ? 1 : 0] = h_ctl_->node_count;
@@ -1308,21 +1608,29 @@ class DeviceEngine : public Engine {
     const u32 g_exp = small ? 24u : expand_grid_;
     const u32 g_wide = small ? 12u : wide_grid_;
     const u32 g_hist = small ? 4u : (u32)num_sms_ * 4;
-    const u32 g_sort = small ? 12u : (u32)num_sms_ * 6;
+    const u32 g_sort = small ? 12u : (u32)num_sms_ * 2;
     switch (stage) {
       case 0:
         k_pass_begin<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         for (int lvl = 0; lvl < max_len; lvl++) k_expand<<<g_exp, EXP_THREADS, EXP_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_);
         break;
       case 1:
+        if (small == 2) {
+          k_small_post<<<1, SP_THREADS, SP_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+          break;
+        }
         k_form_bounds<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_);
         k_form_scan<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         k_reorder<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_);
         k_rs_hist_all<<<g_hist, RS_THREADS, 0, st_>>>(d_ptrs_, d_ctl_);
         for (int pass = 0; pass < 8; pass++)
-          k_rs_onesweep<<<g_sort, RS_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_, pass);
+          k_rs_onesweep<<<g_sort, RS_THREADS, RS_DYN_SMEM, st_>>>(d_ptrs_, d_ctl_, d_tab_, pass);
         break;
       case 2:
+        if (small == 2) {
+          k_merge_old<<<48u, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+          break;
+        }
         k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_match<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
@@ -1330,7 +1638,7 @@ class DeviceEngine : public Engine {
         break;
       default:
         k_refine<<<small ? 8 : 64, 64, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
-        k_pass_end<<<1, 32, 0, st_>>>(d_ctl_, d_tab_);
+        k_pass_end<<<1, 128, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         break;
     }
   }
@@ -1348,7 +1656,7 @@ class DeviceEngine : public Engine {
       if (!use_graphs_) {
         enqueue_stage(stage, max_len, small);
       } else {
-        const int key = ((stage == 0) ? max_len : -stage) * 2 + (small ? 1 : 0) + 1000;
+        const int key = ((stage == 0) ? max_len : -stage) * 4 + ((stage == 0 && small == 2) ? 1 : small) + 1000;
         auto it = graphs_.find(key);
         if (it == graphs_.end()) {
           cudaGraph_t g;
@@ -1364,7 +1672,7 @@ class DeviceEngine : public Engine {
       }
       CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
     }
-    const unsigned long long k1 = (unsigned long long)max_len + 1, k2 = 12, k3 = 4, k4 = 2;
+    const unsigned long long k1 = (unsigned long long)max_len + 1, k2 = (small == 2) ? 1 : 12, k3 = (small == 2) ? 1 : 4, k4 = 2;
     kernel_launches += k1 + k2 + k3 + k4;
     stage_launches[0] += k1; stage_launches[1] += k2; stage_launches[2] += k3; stage_launches[3] += k4;
   }
@@ -1403,7 +1711,7 @@ class DeviceEngine : public Engine {
   void upload_ptrs() {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
     DevPtrs& h = *h_ptrs_;
-    h.P = d_P_; h.forms = forms_.p; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.surv = surv_.p;
+    h.P = d_P_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.surv = surv_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
     h.form_first = form_[0].p; h.form_cnt = form_[1].p; h.form_base = form_[2].p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.events = events_.p; h.tiles = tiles_.p; h.staged = staged_.p;
@@ -1415,13 +1723,18 @@ class DeviceEngine : public Engine {
   cudaStream_t st_;
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
-  bool use_graphs_ = true;
+  bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false;
   std::map<int, cudaGraphExec_t> graphs_;
   RiesParams* d_P_ = 0;
-  PassCtl* d_ctl_ = 0;
+  PassOut* d_out_ = 0;
+  PassOut* h_out_ = 0;
+  PassCtl* d_ctl_ = 0; /* = &d_out_->ctl */
   PassCtl* h_ctl_ = 0;
+  unsigned char* d_passin_ = 0; /* PassArgs, then the forms */
+  unsigned char* h_passin_ = 0;
   PassArgs* d_args_ = 0;
   PassArgs* h_args_ = 0;
+  FormDesc* d_forms_ = 0;
   TableState* d_tab_ = 0;
   DevPtrs* d_ptrs_ = 0;
   DevPtrs* h_ptrs_ = 0;
@@ -1429,9 +1742,7 @@ class DeviceEngine : public Engine {
   SortCtl* d_sortctl_ = 0;
   u64* d_opcnt_ = 0;
   cudaEvent_t ev_[5];
-  DevBuf<FormDesc> forms_;
   FormDesc* h_forms_ = 0;
-  size_t h_forms_cap_ = 0;
   DevBuf<Node> nodes_;
   DevBuf<Row> done_, surv_;
   DevBuf<uint16_t> done_form_;

@@ -93,6 +93,21 @@ def test_gpu_node_arena_regrow(product_lib):
     assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(case["name"])
 
 
+@pytest.mark.parametrize("env_extra", [{"RIES_NO_SMALL_POST": "1"}, {"RIES_FORCE_SMALL_POST": "1"},
+                                       {"RIES_NO_GRAPHS": "1"}],
+                         ids=["general-kernels-only", "mispredicted-small-pass", "no-graphs"])
+def test_gpu_pass_variants_agree(product_lib, env_extra):
+    """Small passes run through a fused single-block kernel, the rest through the general kernels, and a
+    wrong size prediction is rerun: every route must print the same bytes."""
+    import subprocess
+    env = dict(os.environ, HOME="/nonexistent", **env_extra)
+    exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
+    for name in ("t25063_l3_F3_x", "i143_l3", "neg_l2"):
+        case = [c for c in golden_cases() if c["name"] == name][0]
+        r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+        assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(name)
+
+
 def test_gpu_batch_of_targets_matches_reference(product_lib, oracle_build):
     """BASELINE config 5 in miniature: a batch of seeded random targets searched concurrently (8 engines on
     one GPU) must print, per target, exactly what the reference prints for that target alone."""
