@@ -14,6 +14,9 @@
 #include <sys/time.h>
 
 #include <algorithm>
+#include <future>
+#include <map>
+#include <memory>
 
 #include "core/exec.h"
 #include "host/ries_host.h"
@@ -355,6 +358,34 @@ struct Search {
   const MatchEvent* cur_ev = 0;
 
   Search(Options& o, Engine& e, const Sink& s) : opt(o), eng(e), out(s) { t_start = now_sec(); }
+  ~Search() { if (ahead.valid()) ahead.wait(); }
+
+  /* The forms of a complexity do not depend on the side, and the passes visit complexities 1,2,3,... on
+     each side: every list is built once, and the next one is built on a helper thread while the device
+     runs the current pass (gen_forms only reads the immutable parameter block). */
+  struct FormList { std::vector<FormDesc> forms; double n_leaf = 0; };
+  std::map<int, std::unique_ptr<FormList>> form_cache;
+  std::future<std::unique_ptr<FormList>> ahead;
+  int ahead_cplx = -1;
+  std::unique_ptr<FormList> build_forms(int cplx) const {
+    std::unique_ptr<FormList> f(new FormList());
+    gen_forms(S.P, cplx, cplx, f->forms, &f->n_leaf);
+    return f;
+  }
+  const std::vector<FormDesc>& forms_for(int cplx, double* n_leaf) {
+    if (ahead.valid() && (ahead_cplx == cplx || form_cache.size() > 4096)) {
+      form_cache[ahead_cplx] = ahead.get();
+    }
+    auto it = form_cache.find(cplx);
+    if (it == form_cache.end()) it = form_cache.emplace(cplx, build_forms(cplx)).first;
+    if (!ahead.valid() && !form_cache.count(cplx + 1)) {
+      ahead_cplx = cplx + 1;
+      const int c = cplx + 1;
+      ahead = std::async(std::launch::async, [this, c]() { return build_forms(c); });
+    }
+    if (n_leaf) *n_leaf = it->second->n_leaf;
+    return it->second->forms;
+  }
 
   std::string sym_chars(const Sym128& s) const {
     std::string r;
@@ -791,7 +822,6 @@ struct Search {
 
     eng.begin(S.P);
     bool reported_exhaustion = false;
-    std::vector<FormDesc> forms;
     PassOutput po;
     bool going = true;
     while (going) {
@@ -801,7 +831,7 @@ struct Search {
       else { lmin++; lmax++; using_x = 1; cplx = lmax; }
       double genf = 0;
       double tf0 = now_sec();
-      gen_forms(S.P, cplx, cplx, forms, &genf);
+      const std::vector<FormDesc>& forms = forms_for(cplx, &genf);
       po = PassOutput();
       cur_ev = 0;
       double tf1 = now_sec();
