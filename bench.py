@@ -320,9 +320,20 @@ def main():
             execs += c["rhs"] + c["lhs"]
     fp64_peak = ries_b200.fp64_peak_tflops()
     fp64_ach = flops / (dev_ms[0] / 1e3) / 1e12 if dev_ms[0] > 0 else 0.0
+    # DRAM traffic of the dominant kernel: not measurable outside a profiler, so it is taken from the committed
+    # ncu capture of this same workload (tools/gpu_profile.sh -> profiles/), per launch like `achieved`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_l6_k_expand_traffic.json")
+    if dom[0].startswith("K1") and args.workload == "search" and args.target == DEFAULT_TARGET \
+            and args.level == DEFAULT_LEVEL and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_src = "profiles/r1_l6_k_expand_traffic.json: ncu dram__bytes_read.sum+dram__bytes_write.sum over the %d k_expand launches of one search (cold process), per launch" % tj["launches"]
     roofline = {
         "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+        "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+        "algorithmic_bytes_per_launch": (dom[1] / dom[3]) if dom[3] else None,
         "algorithmic_bytes_per_step": dom[1] / args.steps, "launches_per_step": dom[3] / args.steps,
         "avg_launch_ms": dom[2] / dom[3] if dom[3] else None,
         "stage_ms_per_step": {"K1_enum_eval": dev_ms[0] / args.steps, "K2_sort": dev_ms[1] / args.steps,
