@@ -50,6 +50,8 @@ typedef struct ries_run_stats {
      the symbol, counted separately for RHS passes (value only) and LHS passes (value + d/dx) */
   char op_char[48];
   unsigned long long op_count_rhs[48], op_count_lhs[48];
+  /* one search over several GPUs (ries_dist_init): passes whose K1 ran sharded, bytes all-gathered */
+  unsigned long long sharded_passes, gather_bytes;
 } ries_run_stats;
 void ries_last_stats(ries_run_stats *out);
 
@@ -62,6 +64,20 @@ void ries_last_stats(ries_run_stats *out);
 typedef void (*ries_batch_done_fn)(void *ctx, int index, int exit_code, const char *text, size_t n);
 int ries_batch(int n_targets, const char *const *targets, int n_flags, const char *const *flags,
                int n_workers, ries_batch_done_fn done, void *ctx);
+
+/* ONE search sharded over the GPUs of one box (north_star row (e); the reference is single-threaded, there is
+ * nothing to cite): one process per GPU, each calls ries_main() with the same argv after joining an NCCL
+ * communicator.  The forms of every large pass are dealt round-robin to the ranks for enumerate+evaluate,
+ * the ranks' complete expressions are all-gathered over NVLink in rank-major order, and the rest of the pass
+ * runs replicated, so every rank prints the identical report.  NCCL is bound at run time (libnccl.so.2).
+ *   rank 0:      ries_dist_unique_id(id)  -> hand the 128 bytes to the other ranks (any side channel)
+ *   every rank:  ries_dist_init(rank, world, id)   after selecting its GPU (RIES_DEVICE)
+ *   ...          ries_main(...) as usual
+ *   every rank:  ries_dist_finalize()
+ * Return 0 on success. */
+int ries_dist_unique_id(unsigned char id[128]);
+int ries_dist_init(int rank, int world, const unsigned char id[128]);
+void ries_dist_finalize(void);
 
 /* Measured fp64 FMA throughput of the device (TFLOP/s, a short DFMA microbenchmark on the engine's
  * stream): the denominator bench.py uses for K1's fp64 figure.  0 without a GPU. */

@@ -28,6 +28,7 @@ class _Stats(ctypes.Structure):
         ("expand_nodes", ctypes.c_ulonglong),
         ("op_char", ctypes.c_char * 48), ("op_count_rhs", ctypes.c_ulonglong * 48),
         ("op_count_lhs", ctypes.c_ulonglong * 48),
+        ("sharded_passes", ctypes.c_ulonglong), ("gather_bytes", ctypes.c_ulonglong),
     ]
 
 
@@ -49,6 +50,12 @@ def _load():
         lib.ries_last_stats.restype = None
         lib.ries_fp64_peak_tflops.argtypes = []
         lib.ries_fp64_peak_tflops.restype = ctypes.c_double
+        lib.ries_dist_unique_id.argtypes = [ctypes.c_char_p]
+        lib.ries_dist_unique_id.restype = ctypes.c_int
+        lib.ries_dist_init.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        lib.ries_dist_init.restype = ctypes.c_int
+        lib.ries_dist_finalize.argtypes = []
+        lib.ries_dist_finalize.restype = None
         lib.ries_engine_name.argtypes = []
         lib.ries_engine_name.restype = ctypes.c_char_p
         _lib = lib
@@ -124,3 +131,24 @@ def fp64_peak_tflops():
 
 def engine_name():
     return _load().ries_engine_name().decode()
+
+
+def dist_unique_id():
+    """Rank 0: a fresh 128-byte NCCL id for `dist_init` (hand it to the other ranks over any side channel)."""
+    buf = ctypes.create_string_buffer(128)
+    rc = _load().ries_dist_unique_id(buf)
+    if rc != 0:
+        raise RiesError("ries_dist_unique_id failed (%d)" % rc)
+    return buf.raw
+
+
+def dist_init(rank, world, unique_id):
+    """Every rank (one process per GPU, RIES_DEVICE already set): join the communicator.  Afterwards every
+    rank calls `call_main` with the same arguments and they search together (large passes are sharded)."""
+    rc = _load().ries_dist_init(int(rank), int(world), bytes(unique_id))
+    if rc != 0:
+        raise RiesError("ries_dist_init failed (%d)" % rc)
+
+
+def dist_finalize():
+    _load().ries_dist_finalize()

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/ries_b200.h"
+#include "host/dist.h"
 #include "host/ries_host.h"
 
 namespace ries {
@@ -50,6 +51,8 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
     g_last.sort_keys = r.sort_keys;
     g_last.merge_rows = r.merge_rows;
     g_last.expand_nodes = r.expand_nodes;
+    g_last.sharded_passes = r.sharded_passes;
+    g_last.gather_bytes = r.gather_bytes;
     for (int i = 0; i < 48; i++) {
       g_last.op_char[i] = (char)r.op_char[i];
       g_last.op_count_rhs[i] = r.op_count[0][i];
@@ -71,6 +74,17 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
 extern "C" void ries_last_stats(ries_run_stats* out) {
   if (out) *out = g_last;
 }
+
+extern "C" int ries_dist_unique_id(unsigned char id[128]) { return ries::dist_unique_id(id); }
+
+extern "C" int ries_dist_init(int rank, int world, const unsigned char id[128]) {
+  /* the communicator binds to the current device: select it the way the engine will */
+  const char* dev_env = getenv("RIES_DEVICE");
+  if (cudaSetDevice(dev_env ? atoi(dev_env) : 0) != cudaSuccess) return -2;
+  return ries::dist_init(rank, world, id);
+}
+
+extern "C" void ries_dist_finalize(void) { ries::dist_finalize(); }
 
 extern "C" double ries_fp64_peak_tflops(void) {
   try {

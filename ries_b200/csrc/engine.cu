@@ -32,6 +32,7 @@
 
 #include "core/expand.h"
 #include "core/refine.h"
+#include "host/dist.h"
 #include "host/ries_host.h"
 
 namespace ries {
@@ -72,6 +73,9 @@ struct PassArgs {
   int using_x, cplx, skip_exact, nforms;
   double best_match0;
   u32 cap_nodes, cap_done, cap_events, pad;
+  /* one search over several GPUs: this rank enumerates the forms f with f % shard_world == shard_rank, and
+     the regroup kernels read the all-gathered complete expressions instead of this rank's own */
+  int shard_rank, shard_world, gathered, pad2;
 };
 
 /* Written by the kernels of a pass; copied back to pinned host memory at its end. */
@@ -114,6 +118,8 @@ struct DevPtrs {
   Node* nodes;
   Row* done;
   uint16_t* done_form;
+  Row* gdone;           /* all ranks' complete expressions, rank-major (sharded passes only) */
+  uint16_t* gdone_form;
   Row* surv;
   u64* keys[2];
   u32* idx[2];
@@ -137,19 +143,23 @@ struct DevPtrs {
 
 __global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   const u32 nforms = (u32)A->nforms;
-  for (u32 i = threadIdx.x; i < nforms; i += blockDim.x) {
+  const u32 world = (u32)A->shard_world, rank = (u32)A->shard_rank;
+  const u32 nroots = (nforms > rank) ? (nforms - rank + world - 1) / world : 0; /* forms dealt round-robin */
+  for (u32 j = threadIdx.x; j < nroots; j += blockDim.x) {
     Node r;
     r.val = 0; r.der = 0; r.sym.lo = 0; r.sym.hi = 0;
-    r.below = RIES_NO_NODE; r.form = (uint16_t)i; r.cplx = 0; r.tag = 0; r.len = 0; r.sp = 0;
+    r.below = RIES_NO_NODE; r.form = (uint16_t)(rank + j * world); r.cplx = 0; r.tag = 0; r.len = 0; r.sp = 0;
     r.pad0 = 0; r.pad1 = 0;
-    D->nodes[i] = r;
+    D->nodes[j] = r;
+  }
+  for (u32 i = threadIdx.x; i < nforms; i += blockDim.x) {
     D->form_first[i] = 0;
     D->form_cnt[i] = 0;
   }
   u32* sc = (u32*)D->sortctl;
   for (u32 i = threadIdx.x; i < sizeof(SortCtl) / 4; i += blockDim.x) sc[i] = 0;
   if (threadIdx.x == 0) {
-    C->lvl_begin = 0; C->lvl_end = nforms; C->node_count = nforms; C->done_count = 0;
+    C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
     C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
     C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0;
     u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
@@ -498,10 +508,10 @@ __global__ void k_dfma_peak(double* out, int iters) {
    completes at exactly one level, so a form's expressions are contiguous in done[]. */
 __device__ __forceinline__ bool pass_ok(const PassCtl* C) { return (C->overflow & (OVF_NODES | OVF_DONE)) == 0; }
 
-__global__ void k_form_bounds(const DevPtrs* Dp, const PassCtl* C) {
+__global__ void k_form_bounds(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
-  const uint16_t* done_form = Dp->done_form;
+  const uint16_t* done_form = A->gathered ? Dp->gdone_form : Dp->done_form;
   u32* form_first = Dp->form_first;
   u32* form_cnt = Dp->form_cnt;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -549,14 +559,16 @@ __device__ __forceinline__ u64 key_of(double v) { /* order-preserving map double
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
-__global__ void k_reorder(const DevPtrs* Dp, const PassCtl* C) {
+__global__ void k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
   const DevPtrs D = *Dp;
+  const Row* __restrict__ done = A->gathered ? D.gdone : D.done;
+  const uint16_t* __restrict__ done_form = A->gathered ? D.gdone_form : D.done_form;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint16_t f = D.done_form[i];
+    uint16_t f = done_form[i];
     u32 pos = D.form_base[f] + (i - D.form_first[f]);
-    Row r = D.done[i];
+    Row r = done[i];
     D.surv[pos] = r;
     D.keys[0][pos] = key_of(r.val);
     D.idx[0][pos] = pos;
@@ -1102,12 +1114,14 @@ k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState*
   const DevPtrs D = *Dp;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   /* insertion order: stable sort of the done[] indices by form */
-  for (u32 i = tid; i < n; i += SP_THREADS) { s_keys[i] = D.done_form[i]; s_pays[i] = i; }
+  const Row* __restrict__ done = A->gathered ? D.gdone : D.done;
+  const uint16_t* __restrict__ done_form = A->gathered ? D.gdone_form : D.done_form;
+  for (u32 i = tid; i < n; i += SP_THREADS) { s_keys[i] = done_form[i]; s_pays[i] = i; }
   __syncthreads();
   small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 0);
   if (A->nforms > 256) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 8);
   for (u32 j = tid; j < n; j += SP_THREADS) {
-    const Row r = D.done[s_pays[j]];
+    const Row r = done[s_pays[j]];
     D.surv[j] = r;
     s_keys[j] = key_of(r.val);
     s_pays[j] = j;
@@ -1417,6 +1431,8 @@ class DeviceEngine : public Engine {
     h_args_ = (PassArgs*)h_passin_;
     h_forms_ = (FormDesc*)(h_passin_ + PASSIN_FORMS_OFFSET);
     CUDA_CHECK(cudaMallocHost(&h_ptrs_, sizeof(DevPtrs)));
+    CUDA_CHECK(cudaMallocHost(&h_allctl_, 64 * sizeof(PassCtl)));
+    if (const char* e = getenv("RIES_SHARD_MIN")) shard_min_ = (u32)atol(e);
     memset(h_ptrs_, 0, sizeof(DevPtrs));
     for (int i = 0; i < 5; i++) CUDA_CHECK(cudaEventCreate(&ev_[i]));
     const char* arena_env = getenv("RIES_ARENA_CAP"); /* test hook: start tiny to exercise overflow-and-rerun */
@@ -1436,8 +1452,9 @@ class DeviceEngine : public Engine {
     for (int b = 0; b < 2; b++) { keys_[b].release(st_); idx_[b].release(st_); trow_[b].release(st_); tval_[b].release(st_); }
     for (int i = 0; i < 3; i++) form_[i].release(st_);
     uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); tiles_.release(st_); staged_.release(st_);
-    rs_state_.release(st_); cc_state_.release(st_);
+    rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_); allctl_.release(st_);
     cudaStreamSynchronize(st_);
+    cudaFreeHost(h_allctl_);
     cudaFree(d_P_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
     cudaFree(d_opcnt_);
     cudaFreeHost(h_out_); cudaFreeHost(h_passin_); cudaFreeHost(h_ptrs_);
@@ -1464,6 +1481,7 @@ class DeviceEngine : public Engine {
     d2h_bytes = 0;
     for (int i = 0; i < 4; i++) { stage_ms[i] = 0; stage_launches[i] = 0; }
     sort_keys = merge_rows = expand_nodes = 0;
+    sharded_passes = gather_bytes = 0;
   }
 
   long inserted_before(uint32_t seq, bool inclusive) override {
@@ -1503,18 +1521,42 @@ class DeviceEngine : public Engine {
       h_args_->cap_nodes = (u32)std::min<size_t>(nodes_.cap, 0xffffffffu);
       h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
       h_args_->cap_events = (u32)events_.cap; h_args_->pad = 0;
-      CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
-                                 cudaMemcpyHostToDevice, st_));
       /* size class from the previous pass of the same side (sizes grow ~1.3-1.6x per complexity step) */
       int small = (prev_nodes_[using_x ? 1 : 0] <= 12000 && prev_done_[using_x ? 1 : 0] <= 3000) ? 1 : 0;
       if (small && !no_small_post && prev_done_[using_x ? 1 : 0] <= SP_CAP / 3 && nt_ <= 200000u) small = 2;
       if (force_small_post_ && !no_small_post) small = 2; /* test hook: mispredict, to exercise the rerun */
-      launch_pass(max_len, small);
-      CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
-      CUDA_CHECK(cudaStreamSynchronize(st_));
-      CUDA_CHECK(cudaGetLastError());
-      d2h_bytes += sizeof(PassOut);
-      collect_pass_times();
+      /* one search over several GPUs: only passes big enough to pay for the exchange are sharded */
+      const DistState& ds = dist_state();
+      const int shard_world = ds.fake_world > 1 ? ds.fake_world : ds.world;
+      const bool shard = shard_world > 1 && prev_done_[using_x ? 1 : 0] >= shard_min_;
+      h_args_->shard_rank = (shard && ds.fake_world <= 1) ? ds.rank : 0;
+      h_args_->shard_world = shard ? shard_world : 1; h_args_->gathered = shard ? 1 : 0;
+      h_args_->pad2 = 0;
+      CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
+                                 cudaMemcpyHostToDevice, st_));
+      if (!shard) {
+        launch_stages(0, 3, max_len, small);
+        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        CUDA_CHECK(cudaGetLastError());
+        d2h_bytes += sizeof(PassOut);
+        collect_stage_times(0, 3);
+      } else {
+        size_t want_nodes = nodes_.cap, want_done = done_.cap;
+        const u32 fovf = sharded_front(max_len, small, &want_nodes, &want_done);
+        if (fovf) {
+          grow_arena(std::max(want_nodes, nodes_.cap * ((fovf & OVF_NODES) ? 2 : 1)),
+                     std::max(want_done, done_.cap * ((fovf & OVF_DONE) ? 2 : 1)));
+          continue;
+        }
+        sharded_passes++;
+        launch_stages(1, 3, max_len, small);
+        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        CUDA_CHECK(cudaGetLastError());
+        d2h_bytes += sizeof(PassOut);
+        collect_stage_times(1, 3);
+      }
       const u32 ovf = h_ctl_->overflow;
       if (!ovf) break;
       /* grow what overflowed and rerun the pass; the live table buffer has not been touched */
@@ -1570,6 +1612,8 @@ class DeviceEngine : public Engine {
   unsigned long long sort_keys = 0;      /* survivors that went through the radix sort */
   unsigned long long merge_rows = 0;     /* rows written by the merges (old + new) */
   unsigned long long expand_nodes = 0;   /* live prefixes expanded (= exec'd prefixes) */
+  unsigned long long sharded_passes = 0; /* passes whose K1 ran sharded over the ranks */
+  unsigned long long gather_bytes = 0;   /* bytes this rank received/kept in the all-gathers */
   u32 table_rows() const { return nt_; }
   unsigned char sym_chars_[RIES_MAX_SYMS];
   void read_opcounts(unsigned long long* out /* [2][RIES_MAX_SYMS] */) {
@@ -1619,9 +1663,9 @@ class DeviceEngine : public Engine {
           k_small_post<<<1, SP_THREADS, SP_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
           break;
         }
-        k_form_bounds<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_);
+        k_form_bounds<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         k_form_scan<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
-        k_reorder<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_);
+        k_reorder<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         k_rs_hist_all<<<g_hist, RS_THREADS, 0, st_>>>(d_ptrs_, d_ctl_);
         for (int pass = 0; pass < 8; pass++)
           k_rs_onesweep<<<g_sort, RS_THREADS, RS_DYN_SMEM, st_>>>(d_ptrs_, d_ctl_, d_tab_, pass);
@@ -1643,16 +1687,19 @@ class DeviceEngine : public Engine {
     }
   }
 
-  void launch_pass(int max_len, int small) {
-    epoch_host_ = (epoch_host_ + 16) & 0x3ffffff0u; /* what k_pass_begin does to TableState::epoch */
-    if (epoch_host_ == 0) {
-      /* 2^26 passes later the tags wrap: clear the look-back state so old tags cannot alias new ones */
-      epoch_host_ = 16;
-      CUDA_CHECK(cudaMemsetAsync(rs_state_.p, 0, rs_state_.cap * sizeof(u64), st_));
-      CUDA_CHECK(cudaMemsetAsync(cc_state_.p, 0, cc_state_.cap * sizeof(u64), st_));
+  /* Stages [first, last] of a pass on the stream; ev_[k] is recorded before stage k (and after the last). */
+  void launch_stages(int first, int last, int max_len, int small) {
+    if (first == 0) {
+      epoch_host_ = (epoch_host_ + 16) & 0x3ffffff0u; /* what k_pass_begin does to TableState::epoch */
+      if (epoch_host_ == 0) {
+        /* 2^26 passes later the tags wrap: clear the look-back state so old tags cannot alias new ones */
+        epoch_host_ = 16;
+        CUDA_CHECK(cudaMemsetAsync(rs_state_.p, 0, rs_state_.cap * sizeof(u64), st_));
+        CUDA_CHECK(cudaMemsetAsync(cc_state_.p, 0, cc_state_.cap * sizeof(u64), st_));
+      }
     }
-    CUDA_CHECK(cudaEventRecord(ev_[0], st_));
-    for (int stage = 0; stage < 4; stage++) {
+    CUDA_CHECK(cudaEventRecord(ev_[first], st_));
+    for (int stage = first; stage <= last; stage++) {
       if (!use_graphs_) {
         enqueue_stage(stage, max_len, small);
       } else {
@@ -1671,18 +1718,104 @@ class DeviceEngine : public Engine {
         CUDA_CHECK(cudaGraphLaunch(it->second, st_));
       }
       CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
+      const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1
+                                 : (stage == 1) ? ((small == 2) ? 1 : 12)
+                                 : (stage == 2) ? ((small == 2) ? 1 : 4) : 2;
+      kernel_launches += k;
+      stage_launches[stage] += k;
     }
-    const unsigned long long k1 = (unsigned long long)max_len + 1, k2 = (small == 2) ? 1 : 12, k3 = (small == 2) ? 1 : 4, k4 = 2;
-    kernel_launches += k1 + k2 + k3 + k4;
-    stage_launches[0] += k1; stage_launches[1] += k2; stage_launches[2] += k3; stage_launches[3] += k4;
   }
 
-  void collect_pass_times() {
-    for (int i = 0; i < 4; i++) {
+  void collect_stage_times(int first, int last) {
+    for (int i = first; i <= last; i++) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]) == cudaSuccess) stage_ms[i] += ms;
     }
     (void)cudaGetLastError();
+  }
+
+  /* K1 of a pass sharded over `world` ranks (or virtual ranks), then the all-gather of the complete
+     expressions into gdone/gdone_form in rank-major order and the totals into the device control block.
+     Returns the overflow flags (any rank's); on overflow nothing was gathered and *want_* hold the sizes to
+     grow to.  Every rank computes the same totals, so every rank takes the same decisions afterwards. */
+  u32 sharded_front(int max_len, int small, size_t* want_nodes, size_t* want_done) {
+    const DistState& ds = dist_state();
+    const bool fake = ds.fake_world > 1;
+    const int world = fake ? ds.fake_world : ds.world;
+    std::vector<PassCtl> all((size_t)world);
+    if (fake) {
+      /* test hook: the virtual ranks run one after the other on this GPU; the "all-gather" is a copy */
+      size_t off = 0;
+      u32 ovf = 0;
+      for (int r = 0; r < world; r++) {
+        h_args_->shard_rank = r;
+        CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET, cudaMemcpyHostToDevice, st_));
+        launch_stages(0, 0, max_len, small);
+        CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        collect_stage_times(0, 0);
+        all[r] = *h_ctl_;
+        ovf |= h_ctl_->overflow;
+        if (h_ctl_->overflow) break;
+        const size_t c = h_ctl_->done_count;
+        if (off + c > done_.cap) { ovf |= OVF_DONE; *want_done = std::max(*want_done, (off + c) * 2); break; }
+        if (gdone_.ensure(off + c, st_, true)) ptrs_dirty_ = true;
+        if (gdone_form_.ensure(off + c, st_, true)) ptrs_dirty_ = true;
+        if (c) {
+          CUDA_CHECK(cudaMemcpyAsync(gdone_.p + off, done_.p, c * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
+          CUDA_CHECK(cudaMemcpyAsync(gdone_form_.p + off, done_form_.p, c * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
+        }
+        off += c;
+      }
+      if (ovf) {
+        for (int r = 0; r < world; r++) {
+          if (all[r].overflow & OVF_NODES) *want_nodes = std::max(*want_nodes, (size_t)all[r].node_count * 2);
+          if (all[r].overflow & OVF_DONE) *want_done = std::max(*want_done, (size_t)all[r].done_count * 2);
+        }
+        return ovf;
+      }
+    } else {
+      launch_stages(0, 0, max_len, small);
+      allctl_.ensure((size_t)world, st_); /* not in the pointer table */
+      dist_allgather(d_ctl_, allctl_.p, sizeof(PassCtl), st_);
+      CUDA_CHECK(cudaMemcpyAsync(h_allctl_, allctl_.p, (size_t)world * sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      collect_stage_times(0, 0);
+      d2h_bytes += (size_t)world * sizeof(PassCtl);
+      u32 ovf = 0;
+      size_t total = 0;
+      for (int r = 0; r < world; r++) {
+        all[r] = h_allctl_[r];
+        ovf |= all[r].overflow;
+        total += all[r].done_count;
+        if (all[r].overflow & OVF_NODES) *want_nodes = std::max(*want_nodes, (size_t)all[r].node_count * 2);
+        if (all[r].overflow & OVF_DONE) *want_done = std::max(*want_done, (size_t)all[r].done_count * 2);
+      }
+      if (!ovf && total > done_.cap) { ovf |= OVF_DONE; *want_done = std::max(*want_done, total * 2); }
+      if (ovf) return ovf;
+      if (gdone_.ensure(total, st_)) ptrs_dirty_ = true;
+      if (gdone_form_.ensure(total, st_)) ptrs_dirty_ = true;
+      std::vector<size_t> bytes((size_t)world), offs((size_t)world);
+      size_t off = 0;
+      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].done_count * sizeof(Row); offs[r] = off * sizeof(Row); off += all[r].done_count; }
+      dist_allgatherv(done_.p, gdone_.p, bytes.data(), offs.data(), st_);
+      off = 0;
+      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].done_count * sizeof(uint16_t); offs[r] = off * sizeof(uint16_t); off += all[r].done_count; }
+      dist_allgatherv(done_form_.p, gdone_form_.p, bytes.data(), offs.data(), st_);
+      gather_bytes += total * (sizeof(Row) + sizeof(uint16_t));
+    }
+    /* totals into the device control block, as if one K1 had produced everything */
+    PassCtl t = all[0];
+    unsigned long long nodes = 0, done = 0, dead = 0;
+    for (int r = 0; r < world; r++) { nodes += all[r].node_count; done += all[r].done_count; dead += all[r].dead; }
+    t.node_count = (u32)std::min<unsigned long long>(nodes, 0xffffffffull);
+    t.done_count = (u32)done;
+    t.dead = dead;
+    t.lvl_begin = t.lvl_end = 0; t.tile_ticket = 0; t.blocks_done = 0;
+    *h_ctl_ = t;
+    CUDA_CHECK(cudaMemcpyAsync(d_ctl_, h_ctl_, sizeof(PassCtl), cudaMemcpyHostToDevice, st_));
+    if (ptrs_dirty_) upload_ptrs();
+    return 0;
   }
 
   /* nodes / done arenas and everything sized by them */
@@ -1711,7 +1844,7 @@ class DeviceEngine : public Engine {
   void upload_ptrs() {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
     DevPtrs& h = *h_ptrs_;
-    h.P = d_P_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.surv = surv_.p;
+    h.P = d_P_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
     h.form_first = form_[0].p; h.form_cnt = form_[1].p; h.form_base = form_[2].p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.events = events_.p; h.tiles = tiles_.p; h.staged = staged_.p;
@@ -1744,8 +1877,11 @@ class DeviceEngine : public Engine {
   cudaEvent_t ev_[5];
   FormDesc* h_forms_ = 0;
   DevBuf<Node> nodes_;
-  DevBuf<Row> done_, surv_;
-  DevBuf<uint16_t> done_form_;
+  DevBuf<Row> done_, surv_, gdone_;
+  DevBuf<uint16_t> done_form_, gdone_form_;
+  DevBuf<PassCtl> allctl_;
+  PassCtl* h_allctl_ = 0; /* pinned, MAX_RANKS entries */
+  u32 shard_min_ = 100000; /* complete expressions in the previous same-side pass from which a pass is sharded */
   DevBuf<u64> tiles_, rs_state_, cc_state_;
   DevBuf<Staged> staged_;
   DevBuf<u32> form_[3];
@@ -1776,6 +1912,8 @@ void device_engine_report(Engine* e, DeviceReport* r) {
   r->sort_keys = d->sort_keys;
   r->merge_rows = d->merge_rows;
   r->expand_nodes = d->expand_nodes;
+  r->sharded_passes = d->sharded_passes;
+  r->gather_bytes = d->gather_bytes;
   r->table_rows = d->table_rows();
   d->read_opcounts(&r->op_count[0][0]);
   memcpy(r->op_char, d->sym_chars_, sizeof(r->op_char));

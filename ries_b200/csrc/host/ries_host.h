@@ -135,6 +135,7 @@ struct DeviceReport {
   double stage_ms[4];
   unsigned long long stage_launches[4];
   unsigned long long sort_keys, merge_rows, expand_nodes, table_rows;
+  unsigned long long sharded_passes, gather_bytes;
   unsigned long long op_count[2][RIES_MAX_SYMS]; /* exec() calls per symbol: [0] RHS passes, [1] LHS passes */
   unsigned char op_char[RIES_MAX_SYMS];
 };
