@@ -183,6 +183,9 @@ def main():
                     help="search: one full-depth search per step (default); batch: BASELINE config 5, many targets")
     ap.add_argument("--batch-size", type=int, default=256, help="targets per step over all ranks (batch workload)")
     ap.add_argument("--workers", type=int, default=8, help="concurrent engines per GPU (batch workload)")
+    ap.add_argument("--shard-search", action="store_true",
+                    help="N>1: all ranks work on ONE search (K1 sharded by forms, NCCL all-gather of the complete "
+                         "expressions; strong scaling) instead of one independent target per rank")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,7 +237,19 @@ def main():
     if args.workload == "batch":
         return batch_workload(args, rank, local_rank, world, dist, torch, ries_b200)
 
-    if world > 1:
+    def join_search_communicator():
+        """ries_dist_init on every rank: the id comes from rank 0 over torch.distributed (plumbing only)."""
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ries_b200.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ries_b200.dist_init(rank, world, uid.cpu().numpy().tobytes())
+
+    sharded = args.shard_search and world > 1
+    if sharded:
+        join_search_communicator()
+        target = args.target
+    elif world > 1:
         target = targets_for(world)[rank]  # independent targets: BASELINE config-5 style sharding
     else:
         target = args.target
@@ -279,8 +294,38 @@ def main():
     nodes = sum(s[1]["expand_nodes"] for s in per_step)
     dev_total_s = sum(dev_ms) / 1e3
 
+    # N>1, default mode: after the independent-target steps, the same ranks also time ONE search together
+    # (north_star's "time-to-full-report at -l6 on N GPUs"); reported beside the weak-scaling value
+    sharded_extra = None
+    if dist is not None and not sharded:
+        join_search_communicator()
+        sargv = [args.target, "-l" + args.level, "-F3", "--no-slow-messages"]
+        for _ in range(2):
+            ries_b200.call_main(sargv)
+        barrier()
+        ts0 = time.perf_counter()
+        for _ in range(args.steps):
+            scode, _stext = ries_b200.call_main(sargv)
+        barrier()
+        swall = time.perf_counter() - ts0
+        sst = ries_b200.last_stats()
+        ries_b200.dist_finalize()
+        tm = torch.tensor([swall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        sexpr = sst["lhs_expressions"] + sst["rhs_expressions"]
+        sharded_extra = {
+            "workload": "ries %s -l%s -F3, ONE search over %d GPUs" % (args.target, args.level, world),
+            "time_to_full_report_s": tm.item() / args.steps, "expr_per_s_e2e": sexpr * args.steps / tm.item(),
+            "sharded_passes": sst["sharded_passes"], "allgather_MB_per_search": sst["gather_bytes"] / 1e6,
+            "stage_ms": sst["stage_ms"], "scaling": "strong",
+            "how": "forms dealt round-robin to ranks for K1; complete expressions all-gathered rank-major over NCCL; "
+                   "sort/dedupe/match/merge replicated; every rank prints the identical report",
+        }
+
     # whole-job numbers: sum of units over ranks, max of time over ranks
     if dist is not None:
+        if sharded:  # every rank holds the totals of the one search: count them once
+            exprs, dead = (exprs, dead) if rank == 0 else (0.0, 0.0)
         t = torch.tensor([exprs, dead, float(launches)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         tmax = torch.tensor([wall, dev_total_s], dtype=torch.float64, device="cuda")
@@ -290,6 +335,8 @@ def main():
     else:
         exprs_all, dead_all, launches_all, wall_all, dev_all = exprs, dead, launches, wall, dev_total_s
 
+    if sharded:
+        ries_b200.dist_finalize()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -352,9 +399,10 @@ def main():
         "unit": "expr/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall_all / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {
-            "workload": workload if world == 1 else "ries <t_rank> -l%s -F3, one independent target per GPU (BASELINE config-5 distribution, seed %d)" % (args.level, BATCH_SEED),
+            "workload": workload if world == 1 else (workload + ", ONE search over %d GPUs (K1 sharded by forms, NCCL all-gather)" % world) if sharded else "ries <t_rank> -l%s -F3, one independent target per GPU (BASELINE config-5 distribution, seed %d)" % (args.level, BATCH_SEED),
             "expressions_per_step": exprs_all / args.steps, "dead_ends_per_step": dead_all / args.steps,
             "l2": "every step rebuilds all device data from scratch; working set (table + survivors + nodes) exceeds the 126 MB L2 at this level",
             "value_is": "expressions / device-busy time (CUDA events over all stages); e2e is the same search timed around the C-ABI call",
@@ -368,6 +416,8 @@ def main():
         "roofline": roofline,
     }
 
+    if sharded_extra is not None:
+        line["sharded_search"] = sharded_extra
     if not args.no_cpu_baseline and world == 1:
         binary, kind = ref_binary()
         if binary:

@@ -20,7 +20,8 @@ struct Api {
   int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = 0;
   int (*CommDestroy)(nccl_comm_t) = 0;
   int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = 0;
-  int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = 0;
+  int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = 0;
+  int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = 0;
   int (*GroupStart)() = 0;
   int (*GroupEnd)() = 0;
   const char* (*GetErrorString)(int) = 0;
@@ -44,7 +45,8 @@ bool load_api() {
   BIND(CommInitRank, "ncclCommInitRank")
   BIND(CommDestroy, "ncclCommDestroy")
   BIND(AllGather, "ncclAllGather")
-  BIND(Broadcast, "ncclBroadcast")
+  BIND(Send, "ncclSend")
+  BIND(Recv, "ncclRecv")
   BIND(GroupStart, "ncclGroupStart")
   BIND(GroupEnd, "ncclGroupEnd")
   BIND(GetErrorString, "ncclGetErrorString")
@@ -111,11 +113,18 @@ void dist_allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStr
 }
 
 void dist_allgatherv(const void* send, void* recv, const size_t* bytes, const size_t* offset, cudaStream_t st) {
+  /* every rank pushes its segment to every peer (one grouped send/recv: direct NVLink copies through the
+     switch, all pairs at once) and copies its own into place */
+  const int me = g_dist.rank;
+  if (bytes[me]) {
+    cudaError_t e = cudaMemcpyAsync((char*)recv + offset[me], send, bytes[me], cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { fprintf(stderr, "ries_b200: gather copy failed: %s\n", cudaGetErrorString(e)); abort(); }
+  }
   check(g_api.GroupStart(), "ncclGroupStart");
-  for (int r = 0; r < g_dist.world; r++) {
-    if (bytes[r] == 0) continue;
-    check(g_api.Broadcast(send, (char*)recv + offset[r], bytes[r], NCCL_INT8, r, (nccl_comm_t)g_dist.comm, st),
-          "ncclBroadcast");
+  for (int d = 1; d < g_dist.world; d++) {
+    const int to = (me + d) % g_dist.world, from = (me - d + g_dist.world) % g_dist.world;
+    if (bytes[me]) check(g_api.Send(send, bytes[me], NCCL_INT8, to, (nccl_comm_t)g_dist.comm, st), "ncclSend");
+    if (bytes[from]) check(g_api.Recv((char*)recv + offset[from], bytes[from], NCCL_INT8, from, (nccl_comm_t)g_dist.comm, st), "ncclRecv");
   }
   check(g_api.GroupEnd(), "ncclGroupEnd");
 }
