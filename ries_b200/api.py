@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libries_b200.so")
+_LIB_PATH = os.environ.get("RIES_B200_LIB") or os.path.join(_HERE, "libries_b200.so")
 _lib = None
 
 _WRITE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_char), ctypes.c_size_t)

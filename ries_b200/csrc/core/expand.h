@@ -71,6 +71,81 @@ RIES_HD bool expand_tests(const RiesParams& P, const FormDesc& F, const Node& pa
   return true;
 }
 
+/* The same tests for ALL candidate slots of a prefix at once, as bit masks (bit k = slot k survives).
+   Per class, host-built tables list the slots by weight bound, by rule-mask bit, the 'x' slot and the
+   slots with an -O limit; only the last needs a per-slot look at the prefix.  Must agree with
+   expand_tests() slot by slot (the CPU oracle uses expand_tests; the parity tests compare). */
+struct TestTables {
+  unsigned short wge[3][64];  /* slots whose symbol weight is >= w */
+  unsigned short wle[3][64];  /* ... <= w */
+  unsigned short attr[3][32]; /* slots whose rule mask has attribute bit b */
+  unsigned short xslot[3];    /* slots holding 'x' */
+  unsigned short limited[3];  /* slots whose symbol has an -O count limit */
+};
+
+inline void build_test_tables(const RiesParams& P, TestTables& T) {
+  for (int c = 0; c < 3; c++) {
+    for (int w = 0; w < 64; w++) { T.wge[c][w] = 0; T.wle[c][w] = 0; }
+    for (int b = 0; b < 32; b++) T.attr[c][b] = 0;
+    T.xslot[c] = 0;
+    T.limited[c] = 0;
+    for (int k = 0; k < P.cls_n[c]; k++) {
+      const int g = P.trial[c][k];
+      const int wt = P.sym_wgt[g];
+      for (int w = 0; w < 64; w++) {
+        if (wt >= w) T.wge[c][w] |= (unsigned short)(1u << k);
+        if (wt <= w) T.wle[c][w] |= (unsigned short)(1u << k);
+      }
+      for (int b = 0; b < 32; b++)
+        if ((unsigned)P.sym_mask[g] & (1u << b)) T.attr[c][b] |= (unsigned short)(1u << k);
+      if (P.sym_char[g] == 'x') T.xslot[c] |= (unsigned short)(1u << k);
+      if (P.sym_alwd[g] < RIES_MAX_ELEN) T.limited[c] |= (unsigned short)(1u << k);
+    }
+  }
+}
+
+/* true when every enabled symbol's weight fits the tables (always, short of --symbol-weights) */
+inline bool test_tables_cover(const RiesParams& P) {
+  for (int c = 0; c < 3; c++)
+    for (int k = 0; k < P.cls_n[c]; k++) {
+      const int wt = P.sym_wgt[P.trial[c][k]];
+      if (wt < 0 || wt > 63) return false;
+    }
+  return true;
+}
+
+#ifdef __CUDA_ARCH__
+#define RIES_CTZ(x) (__ffs((int)(x)) - 1)
+#else
+#define RIES_CTZ(x) __builtin_ctz(x)
+#endif
+
+RIES_HD unsigned expand_mask(const RiesParams& P, const TestTables& T, const FormDesc& F, const Node& par,
+                             int cls, int atts, int using_x, int e_minw, int e_maxw) {
+  const int ip = par.len;
+  const int whi = e_maxw - F.rminw[ip + 1] - par.cplx; /* weight <= whi  <=>  t_cpx + rminw <= e_maxw */
+  const int wlo = e_minw - F.rmaxw[ip + 1] - par.cplx; /* weight >= wlo  <=>  t_cpx + rmaxw >= e_minw */
+  if (whi < 0 || wlo > 63) return 0;
+  unsigned m = (unsigned)T.wge[cls][wlo < 0 ? 0 : wlo] & (unsigned)T.wle[cls][whi > 63 ? 63 : whi];
+  unsigned a = (unsigned)atts;
+  while (a && m) {
+    const int b = RIES_CTZ(a);
+    a &= a - 1;
+    m &= ~(unsigned)T.attr[cls][b];
+  }
+  if (using_x && ip == 0) m &= T.xslot[cls];
+  unsigned lim = m & T.limited[cls];
+  while (lim) {
+    const int k = RIES_CTZ(lim);
+    lim &= lim - 1;
+    const int g = P.trial[cls][k];
+    int ct = 0;
+    for (int i = 0; i < ip; i++) ct += (sym_get(par.sym, i) == (unsigned)(g + 1));
+    if (ct >= P.sym_alwd[g]) m &= ~(1u << k);
+  }
+  return m;
+}
+
 /* exec of the chosen symbol on the cactus stack (the child's ge_2 entry, 8942-8954), the value prunes
    (8962-9076) and the complete-expression tests (9085-9139).  `nodes` is the pass's node arena
    (parents of every level stay resident for `below` links); `par_idx` is the parent's own index.

@@ -114,6 +114,7 @@ struct TableState {
    so kernel arguments (and the captured graphs) never change. */
 struct DevPtrs {
   const RiesParams* P;
+  const TestTables* tt;
   FormDesc* forms;
   Node* nodes;
   Row* done;
@@ -190,12 +191,16 @@ __global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, Tabl
      phase 3  thread = listed pair: exec + value prunes; warps are (almost) operator-uniform
      phase 4  ordered append: children land in (prefix, symbol) order = the reference's DFS order
    The last block to leave advances the frontier for the next level. */
+#ifndef EXP_THREADS
 #define EXP_THREADS 256
-#define EXP_PARENTS 256
+#endif
+#define EXP_PARENTS EXP_THREADS
 #define EXP_MAX_ITEMS (EXP_PARENTS * RIES_SLOTS)
+#ifndef EXP_MIN_BLOCKS
 #define EXP_MIN_BLOCKS 3
-#define IT_LIVE 0x1000u
-#define IT_DONE 0x2000u
+#endif
+#define IT_LIVE 0x4000u
+#define IT_DONE 0x8000u
 
 #define TS_AGG (1ull << 62)
 #define TS_INC (2ull << 62)
@@ -266,6 +271,7 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
   TileBuf* s_buf = (TileBuf*)s_dyn; /* [2] */
   __shared__ u32 s_opcnt[RIES_MAX_SYMS];
   __shared__ RiesParams P;
+  __shared__ TestTables TT;
   __shared__ u32 s_wcnt[EXP_THREADS / 32][RIES_SLOTS];
   __shared__ u32 s_slot_base[RIES_SLOTS];
   __shared__ u32 s_wl[EXP_THREADS / 32], s_wd[EXP_THREADS / 32];
@@ -283,6 +289,9 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
       const u32* src = (const u32*)D.P;
       u32* dst = (u32*)&P;
       for (u32 i = tid; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];
+      const u32* tsrc = (const u32*)D.tt;
+      u32* tdst = (u32*)&TT;
+      for (u32 i = tid; i < sizeof(TestTables) / 4; i += EXP_THREADS) tdst[i] = tsrc[i];
       if (tid == 0) s_dead = 0;
       if (tid < RIES_MAX_SYMS) s_opcnt[tid] = 0;
     }
@@ -320,10 +329,8 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
             const int cls = F.cls[par.len];
             const int ns = P.cls_n[cls];
             const int atts = prefix_attrs(P, F, par, using_x);
-            for (int k = 0; k < ns; k++) {
-              if (expand_tests(P, F, par, k, atts, using_x, cplx, cplx)) mask |= 1u << k;
-              else my_dead++;
-            }
+            mask = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
+            my_dead += (u32)ns - (u32)__popc(mask);
             B.cls[tid] = (unsigned char)cls;
             B.complete[tid] = (unsigned char)(par.len + 1 >= F.flen);
           }
@@ -425,7 +432,7 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
         for (u32 i = tid; i < T; i += EXP_THREADS) {
           const u32 it = B.item[i];
           if (!(it & (IT_LIVE | IT_DONE))) continue;
-          const u32 pl = (it >> 4) & 255u, k = it & 15u;
+          const u32 pl = (it >> 4) & 1023u, k = it & 15u;
           const Node& par = B.par[pl];
           const int g = P.trial[B.cls[pl]][k];
           const Staged st = staged[i];
@@ -1413,6 +1420,7 @@ class DeviceEngine : public Engine {
     force_small_post_ = getenv("RIES_FORCE_SMALL_POST") != 0;
     CUDA_CHECK(cudaFuncSetAttribute(k_small_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_DYN_SMEM));
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
+    CUDA_CHECK(cudaMalloc(&d_tt_, sizeof(TestTables)));
     CUDA_CHECK(cudaMalloc(&d_out_, sizeof(PassOut)));
     CUDA_CHECK(cudaMemset(d_out_, 0, sizeof(PassOut)));
     d_ctl_ = &d_out_->ctl;
@@ -1455,7 +1463,7 @@ class DeviceEngine : public Engine {
     rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_); allctl_.release(st_);
     cudaStreamSynchronize(st_);
     cudaFreeHost(h_allctl_);
-    cudaFree(d_P_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
+    cudaFree(d_P_); cudaFree(d_tt_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
     cudaFree(d_opcnt_);
     cudaFreeHost(h_out_); cudaFreeHost(h_passin_); cudaFreeHost(h_ptrs_);
     if (h_events_) cudaFreeHost(h_events_);
@@ -1465,7 +1473,13 @@ class DeviceEngine : public Engine {
   const char* name() const override { return "sm_100a"; }
 
   void begin(const RiesParams& P) override {
+    if (!test_tables_cover(P)) {
+      fprintf(stderr, "ries_b200: a symbol weight is outside the test tables' range\n");
+      abort();
+    }
+    build_test_tables(P, h_tt_);
     CUDA_CHECK(cudaMemcpyAsync(d_P_, &P, sizeof(P), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaMemcpyAsync(d_tt_, &h_tt_, sizeof(TestTables), cudaMemcpyHostToDevice, st_));
     CUDA_CHECK(cudaMemsetAsync(d_opcnt_, 0, 2 * RIES_MAX_SYMS * sizeof(u64), st_));
     TableState t0;
     t0.cur = 0; t0.nt = 0; t0.epoch = epoch_host_; t0.pad = 0;
@@ -1844,7 +1858,7 @@ class DeviceEngine : public Engine {
   void upload_ptrs() {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
     DevPtrs& h = *h_ptrs_;
-    h.P = d_P_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
+    h.P = d_P_; h.tt = d_tt_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
     h.form_first = form_[0].p; h.form_cnt = form_[1].p; h.form_base = form_[2].p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.events = events_.p; h.tiles = tiles_.p; h.staged = staged_.p;
@@ -1859,6 +1873,8 @@ class DeviceEngine : public Engine {
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false;
   std::map<int, cudaGraphExec_t> graphs_;
   RiesParams* d_P_ = 0;
+  TestTables* d_tt_ = 0;
+  TestTables h_tt_;
   PassOut* d_out_ = 0;
   PassOut* h_out_ = 0;
   PassCtl* d_ctl_ = 0; /* = &d_out_->ctl */
