@@ -2,7 +2,7 @@
 //
 //   K1  k_expand            enumerate + evaluate one expression position of every live prefix
 //                           [ge_2 + exec, ries.c:8908-9475, 5308-5950]
-//   K2  k_rs_hist_all/k_rs_onesweep   stable LSD radix sort of the pass's survivors on the fp64 value
+//   K2  k_reorder/k_rs_onesweep       stable LSD radix sort of the pass's survivors on the fp64 value
 //       k_classify_compact  duplicate pruning inside the pass and against the resident table
 //       k_merge_new/old     merge into the resident sorted table         [bt_insert, ries.c:8622-8724]
 //   K3  k_match             gap-local neighbour test with the derivative-scaled window
@@ -566,27 +566,44 @@ __device__ __forceinline__ u64 key_of(double v) { /* order-preserving map double
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
-__global__ void k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+/* Survivors into insertion order, their sort keys, and (fused, so the keys are not read again) the
+   histograms of all eight key digits for the radix sort below. */
+__global__ void __launch_bounds__(256)
+k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+  __shared__ u32 s_h[8][256];
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
+  if (blockIdx.x * blockDim.x >= n) return;
   const DevPtrs D = *Dp;
   const Row* __restrict__ done = A->gathered ? D.gdone : D.done;
   const uint16_t* __restrict__ done_form = A->gathered ? D.gdone_form : D.done_form;
+  for (int d = 0; d < 8; d++) s_h[d][threadIdx.x] = 0;
+  __syncthreads();
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint16_t f = done_form[i];
     u32 pos = D.form_base[f] + (i - D.form_first[f]);
     Row r = done[i];
     D.surv[pos] = r;
-    D.keys[0][pos] = key_of(r.val);
+    const u64 k = key_of(r.val);
+    D.keys[0][pos] = k;
     D.idx[0][pos] = pos;
+#pragma unroll
+    for (int d = 0; d < 8; d++) atomicAdd(&s_h[d][(u32)(k >> (8 * d)) & 255u], 1u);
+  }
+  __syncthreads();
+  SortCtl* ctl = D.sortctl;
+  for (int d = 0; d < 8; d++) {
+    u32 c = s_h[d][threadIdx.x];
+    if (c) atomicAdd(&ctl->ghist[d][threadIdx.x], c);
   }
 }
 
 /* ---------------------------------------------------------------- K2: radix sort --------- */
-/* Stable LSD radix sort of (u64 key, u32 payload), 8 digits of 8 bits, "onesweep" style: ONE pass over
-   the keys builds all eight digit histograms; each digit pass is then a single kernel in which every
-   2048-key chunk gets its per-digit output offsets by decoupled look-back over the chunks before it
-   (chunks are taken in ticket order, so equal keys keep their input order = insertion order). */
+/* Stable LSD radix sort of (u64 key, u32 payload), 8 digits of 8 bits, "onesweep" style: the histograms
+   of all eight digits come from k_reorder (which writes the keys); each digit pass is then a single
+   kernel in which every 4096-key chunk gets its per-digit output offsets by decoupled look-back over the
+   chunks before it (chunks are taken in ticket order, so equal keys keep their input order = insertion
+   order). */
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_ITEMS 16
@@ -594,34 +611,6 @@ __global__ void k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C
 #define RS_FLAG_AGG 1ull
 #define RS_FLAG_INC 2ull
 #define RS_DYN_SMEM (RS_CHUNK * (sizeof(u64) + sizeof(u32)))
-
-__global__ void __launch_bounds__(RS_THREADS)
-k_rs_hist_all(const DevPtrs* Dp, const PassCtl* C) {
-  __shared__ u32 s_h[8][256];
-  if (!pass_ok(C)) return;
-  const u32 n = C->done_count;
-  if (blockIdx.x * RS_CHUNK >= n) return;
-  const u64* __restrict__ keys = Dp->keys[0];
-  for (int d = 0; d < 8; d++) s_h[d][threadIdx.x] = 0;
-  __syncthreads();
-  for (u32 base = blockIdx.x * RS_CHUNK; base < n; base += gridDim.x * RS_CHUNK) {
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-      u32 i = base + r * RS_THREADS + threadIdx.x;
-      if (i < n) {
-        u64 k = keys[i];
-#pragma unroll
-        for (int d = 0; d < 8; d++) atomicAdd(&s_h[d][(u32)(k >> (8 * d)) & 255u], 1u);
-      }
-    }
-  }
-  __syncthreads();
-  SortCtl* ctl = Dp->sortctl;
-  for (int d = 0; d < 8; d++) {
-    u32 c = s_h[d][threadIdx.x];
-    if (c) atomicAdd(&ctl->ghist[d][threadIdx.x], c);
-  }
-}
 
 /* One digit pass.  Per 4096-key chunk:
      rank     each warp ranks its own 512 keys (warp-striped, 16 rounds of match_any against a private
@@ -1418,6 +1407,7 @@ class DeviceEngine : public Engine {
     use_graphs_ = getenv("RIES_NO_GRAPHS") == 0;
     use_small_post_ = getenv("RIES_NO_SMALL_POST") == 0; /* test hook: every pass through the general kernels */
     force_small_post_ = getenv("RIES_FORCE_SMALL_POST") != 0;
+    pass_log_ = getenv("RIES_PASS_LOG") != 0; /* one line per pass on stderr: sizes and device time per stage */
     CUDA_CHECK(cudaFuncSetAttribute(k_small_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_DYN_SMEM));
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
     CUDA_CHECK(cudaMalloc(&d_tt_, sizeof(TestTables)));
@@ -1584,6 +1574,13 @@ class DeviceEngine : public Engine {
       if (ovf & OVF_SMALL) no_small_post = true;
     }
     const u32 n = h_ctl_->done_count, nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
+    if (pass_log_) {
+      float ms[4] = {0, 0, 0, 0};
+      for (int i = 0; i < 4; i++) (void)cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]);
+      (void)cudaGetLastError();
+      fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
+              using_x ? "LHS" : "RHS", cplx, nforms, max_len, h_ctl_->node_count, n, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
+    }
     prev_nodes_[using_x ? 1 : 0] = h_ctl_->node_count;
     prev_done_[using_x ? 1 : 0] = n;
     expand_nodes += h_ctl_->node_count;
@@ -1665,7 +1662,6 @@ class DeviceEngine : public Engine {
        exit at once costs more than the work itself.  A wrong prediction is slow, never wrong. */
     const u32 g_exp = small ? 24u : expand_grid_;
     const u32 g_wide = small ? 12u : wide_grid_;
-    const u32 g_hist = small ? 4u : (u32)num_sms_ * 4;
     const u32 g_sort = small ? 12u : (u32)num_sms_ * 2;
     switch (stage) {
       case 0:
@@ -1680,7 +1676,6 @@ class DeviceEngine : public Engine {
         k_form_bounds<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         k_form_scan<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         k_reorder<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
-        k_rs_hist_all<<<g_hist, RS_THREADS, 0, st_>>>(d_ptrs_, d_ctl_);
         for (int pass = 0; pass < 8; pass++)
           k_rs_onesweep<<<g_sort, RS_THREADS, RS_DYN_SMEM, st_>>>(d_ptrs_, d_ctl_, d_tab_, pass);
         break;
@@ -1733,7 +1728,7 @@ class DeviceEngine : public Engine {
       }
       CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
       const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1
-                                 : (stage == 1) ? ((small == 2) ? 1 : 12)
+                                 : (stage == 1) ? ((small == 2) ? 1 : 11)
                                  : (stage == 2) ? ((small == 2) ? 1 : 4) : 2;
       kernel_launches += k;
       stage_launches[stage] += k;
@@ -1870,7 +1865,7 @@ class DeviceEngine : public Engine {
   cudaStream_t st_;
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
-  bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false;
+  bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
   std::map<int, cudaGraphExec_t> graphs_;
   RiesParams* d_P_ = 0;
   TestTables* d_tt_ = 0;
