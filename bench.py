@@ -352,7 +352,7 @@ def main():
     merge_bytes = merge_rows * MERGE_BYTES_PER_ROW + merge_rows * ROW_BYTES
     stages = [
         ("K1 enumerate+evaluate (k_expand)", k1_bytes, dev_ms[0], dev_launches[0]),
-        ("K2 order+radix sort (k_rs_hist_all/k_rs_onesweep)", sort_bytes, dev_ms[1], dev_launches[1]),
+        ("K2 order+radix sort (k_reorder/k_rs_onesweep)", sort_bytes, dev_ms[1], dev_launches[1]),
         ("K2/K3 classify+match+merge (k_classify/k_match/k_merge_*)", merge_bytes, dev_ms[2], dev_launches[2]),
     ]
     dom = max(stages, key=lambda s: s[2])
