@@ -59,6 +59,7 @@ static const char *argv0;
 static double levadj = 2.0, tlevel = 4.0, target = 1.0, exec_x;
 static int got_target, restrict_sub, restrict_exp, restrict_trig, exact_exit, relative_x = 1, wide_out;
 static int show_ss, S_opt, NOS_opt, slow_msg = 1, fmt = 2, debug_y, no_simplify;
+static int one_sided, anagram_opt, preempt_w[256]; /* --one-sided 11600, --numeric-anagram 11586, --symbol-weights 11689 */
 static double max_matches = 100, k_max_match_dist = -0.01, min_matchsize;
 static double k_pi, k_e, k_phi, scale_trig, sig_loss = 0.01, vanished_dx = 1e-6, p_ovr, n_ovr;
 static double best_match, k_min_best_match, init_match_dist, precision_ulp;
@@ -289,7 +290,7 @@ static void report(const char *le, const char *re, double rootv, double delta) {
   char lf[512], rf[512], fval[64], froot[64]; int ll, rl, width, lp, rp, tw, over, posn = 0, i; const char *intro = "for x ";
   if (delta == 0 && got_exact) return;
   fmt_expr(le, lf); fmt_expr(re, rf); ll = (int)strlen(lf); rl = (int)strlen(rf);
-  width = relative_x ? 44 : 40; tw = width + 5; lp = width / 2; rp = width - lp;
+  width = relative_x ? 44 : 40; tw = width + 5; lp = one_sided ? width / 8 : width / 2; rp = width - lp; /* 8113 */
   lp -= ll; if (lp < 0) lp = 0; rp -= rl; if (rp < 0) rp = 0;
   width = lp + ll + 5 + rl + rp;
   while (width > tw && lp > 0) { lp--; width--; }
@@ -547,6 +548,36 @@ static void parse(int argc, char **argv) {
       } else { printf("%s: --max-matches should be followed by a numeric argument.\nexamples:  -n7  or  --max-matches 7\n\n", argv0); help(); print_end(-1); }
     }
     else if (!strcmp(a, "--no-slow-messages")) slow_msg = 0;
+    else if (!strcmp(a, "--one-sided")) one_sided = 1;
+    else if (!strcmp(a, "--numeric-anagram")) {
+      if (i + 1 < argc && argv[i + 1][0] && argv[i + 1][0] != '-') { /* set_anagram 10202 */
+        const char *ana = argv[++i], *as = "123456789efprs"; int k;
+        for (k = 0; as[k]; k++) alwd[(unsigned char)as[k]] = 0;
+        for (k = 0; ana[k]; k++) if (strchr(as, ana[k])) alwd[(unsigned char)ana[k]]++;
+        anagram_opt = 1;
+      } else { printf("%s: --numeric-anagram should be followed by a string of digits.\n\n", argv0); help(); print_end(-1); }
+    }
+    else if (!strcmp(a, "--symbol-weights")) {
+      if (i + 1 < argc && argv[i + 1][0] && argv[i + 1][0] != '-') {
+        while (i + 1 < argc && argv[i + 1][0] && argv[i + 1][0] != '-') {
+          const char *arg = argv[++i]; char tmp[20]; int k = 0; double w;
+          strncpy(tmp, arg, 19); tmp[19] = 0;
+          while (tmp[k] == '.' || (tmp[k] >= '0' && tmp[k] <= '9')) k++;
+          if (tmp[k] == ':' && tmp[k + 1]) {
+            tmp[k++] = 0; w = strtod(tmp, 0);
+            if (w <= 0.0) { printf("%s: Symbol weight may not be %f or less.\n", argv0, 0.0); print_end(-1); }
+            if (w > 100.0) w = 100.0;
+            preempt_w[(unsigned char)tmp[k]] = (int)floor(w + 0.5);
+          } else {
+            printf("%s: --symbol-weights argument syntax is NUMBER:<sym>, for example\n  12:^   to set weight of '^' to 12\n  Instead I got '%s'\n", argv0, arg);
+            print_end(-1);
+          }
+        }
+      } else {
+        printf("%s: --symbol-weights should be followed by one or more tuples\n  of the form NUMBER:<sym>, for example 12:^   to set weight of '^' to 12\n", argv0);
+        print_end(-1);
+      }
+    }
     else if (!strcmp(a, "--any-exponents")) restrict_exp = T_NONE;
     else if (!strcmp(a, "--any-subexpressions")) restrict_sub = T_NONE;
     else if (!strcmp(a, "--any-trig-args")) restrict_trig = T_NONE;
@@ -598,7 +629,7 @@ static void init2(void) {
   if (alwd['W']) { printf("%s: The Lambert W function 'W' requires the stand-alone maths library.\n", argv0); help(); print_end(1); }
   for (i = 0; i < NDEFS; i++) {
     unsigned char c = (unsigned char)DEFS[i].ch; int cl = DEFS[i].seft - 'a';
-    seft_of[c] = DEFS[i].seft; wgt[c] = DEFS[i].w + 10; forth_of[c] = DEFS[i].forth; terse_of[c] = DEFS[i].terse;
+    seft_of[c] = DEFS[i].seft; wgt[c] = preempt_w[c] >= 0 ? preempt_w[c] : DEFS[i].w + 10; /* 9872 */ forth_of[c] = DEFS[i].forth; terse_of[c] = DEFS[i].terse;
     if (alwd[c]) lst[cl][nlst[cl]++] = c;
   }
   if (nlst[0] < 2) { printf("%s: You must allow at least one constant symbol.\n", argv0); if (S_opt) printf("  (Note that the -S option disables all other symbols)\n"); help(); print_end(1); }
@@ -682,7 +713,7 @@ static void print_end(int code) { /* 7574 */
 int main(int argc, char **argv) {
   int i, going = 1, exhausted = 0; double lim_gen, lim_prune; char buf[64]; form F;
   t0 = now(); argv0 = argv[0];
-  for (i = 0; i < 256; i++) alwd[i] = MAXLEN;
+  for (i = 0; i < 256; i++) { alwd[i] = MAXLEN; preempt_w[i] = -1; }
   alwd['W'] = 0;
   for (i = 0; i < NDEFS; i++) { INFIX_NAME[(unsigned char)DEFS[i].ch] = ""; }
   { static const char *nm[][3] = {{"1","1","integer"},{"f","phi",""},{"2","2","integer"},{"e","e",""},{"3","3","integer"},{"p","pi",""},
@@ -694,6 +725,7 @@ int main(int argc, char **argv) {
     for (i = 0; i < (int)(sizeof nm / sizeof nm[0]); i++) { INFIX_NAME[(unsigned char)nm[i][0][0]] = nm[i][1]; DESC[(unsigned char)nm[i][0][0]] = nm[i][2]; } }
   if (argc > 1) parse(argc, argv);
   else { printf("%s: Please specify a target number.\n\n", argv0); help(); print_end(1); }
+  if (anagram_opt) one_sided = 1; /* 12319 */
   init2();
   if (show_ss) {
     show_symset();
@@ -732,7 +764,7 @@ int main(int argc, char **argv) {
   lim_prune = lim_gen * 15.0;
   if (debug_y) printf("Will stop after generating searchmax=%g expressions\n", lim_gen);
   while (going) {                                                                    /* 12396 */
-    double genf; int lhs = !(lhs_insert > rhs_insert);
+    double genf; int lhs = !((one_sided && lhs_insert >= 1) || (lhs_insert > rhs_insert)); /* 12425 */
     g_ne = 0; insert_count = 0; prune_count = 0;
     memset(&F, 0, sizeof F);
     if (!lhs) { rmin++; rmax++; genf = forms(&F, 0, 0, 0, rmin, rmax, 0);
@@ -742,10 +774,11 @@ int main(int argc, char **argv) {
       if (debug_y) printf("finished LHS from {%d} to {%d}: %g forms expanded, %g expressions.\n\n", lmin, lmax, genf, g_ne);
       lhs_gen += g_ne; lhs_insert += insert_count; lhs_prune += prune_count; }
     gen_total += g_ne;
-    if (lmax > exhaust_cpx && rmax > exhaust_cpx) {
+    if (lmax > exhaust_cpx && (one_sided || rmax > exhaust_cpx)) {
       if (num_matches == 0) {
         printf("exhaustion timeout (complexity LHS {%d}, RHS {%d}). Possible causes:\n  MAX_ELEN %d too small\n", lmax, rmax, MAXLEN);
         if (NOS_opt) printf("  too many symbols excluded via -N, -O or -S\n");
+        if (anagram_opt) printf("  --numeric-anagram too restrictive\n");
         printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n");
         exhausted = 1;
       }

@@ -75,9 +75,10 @@ RIES_HD bool expand_tests(const RiesParams& P, const FormDesc& F, const Node& pa
    Per class, host-built tables list the slots by weight bound, by rule-mask bit, the 'x' slot and the
    slots with an -O limit; only the last needs a per-slot look at the prefix.  Must agree with
    expand_tests() slot by slot (the CPU oracle uses expand_tests; the parity tests compare). */
+#define RIES_TT_W 104 /* weights 0..103: --symbol-weights caps a weight at 100 (ries.c:3197) */
 struct TestTables {
-  unsigned short wge[3][64];  /* slots whose symbol weight is >= w */
-  unsigned short wle[3][64];  /* ... <= w */
+  unsigned short wge[3][RIES_TT_W]; /* slots whose symbol weight is >= w */
+  unsigned short wle[3][RIES_TT_W]; /* ... <= w */
   unsigned short attr[3][32]; /* slots whose rule mask has attribute bit b */
   unsigned short xslot[3];    /* slots holding 'x' */
   unsigned short limited[3];  /* slots whose symbol has an -O count limit */
@@ -85,14 +86,14 @@ struct TestTables {
 
 inline void build_test_tables(const RiesParams& P, TestTables& T) {
   for (int c = 0; c < 3; c++) {
-    for (int w = 0; w < 64; w++) { T.wge[c][w] = 0; T.wle[c][w] = 0; }
+    for (int w = 0; w < RIES_TT_W; w++) { T.wge[c][w] = 0; T.wle[c][w] = 0; }
     for (int b = 0; b < 32; b++) T.attr[c][b] = 0;
     T.xslot[c] = 0;
     T.limited[c] = 0;
     for (int k = 0; k < P.cls_n[c]; k++) {
       const int g = P.trial[c][k];
       const int wt = P.sym_wgt[g];
-      for (int w = 0; w < 64; w++) {
+      for (int w = 0; w < RIES_TT_W; w++) {
         if (wt >= w) T.wge[c][w] |= (unsigned short)(1u << k);
         if (wt <= w) T.wle[c][w] |= (unsigned short)(1u << k);
       }
@@ -109,7 +110,7 @@ inline bool test_tables_cover(const RiesParams& P) {
   for (int c = 0; c < 3; c++)
     for (int k = 0; k < P.cls_n[c]; k++) {
       const int wt = P.sym_wgt[P.trial[c][k]];
-      if (wt < 0 || wt > 63) return false;
+      if (wt < 0 || wt >= RIES_TT_W) return false;
     }
   return true;
 }
@@ -125,8 +126,8 @@ RIES_HD unsigned expand_mask(const RiesParams& P, const TestTables& T, const For
   const int ip = par.len;
   const int whi = e_maxw - F.rminw[ip + 1] - par.cplx; /* weight <= whi  <=>  t_cpx + rminw <= e_maxw */
   const int wlo = e_minw - F.rmaxw[ip + 1] - par.cplx; /* weight >= wlo  <=>  t_cpx + rmaxw >= e_minw */
-  if (whi < 0 || wlo > 63) return 0;
-  unsigned m = (unsigned)T.wge[cls][wlo < 0 ? 0 : wlo] & (unsigned)T.wle[cls][whi > 63 ? 63 : whi];
+  if (whi < 0 || wlo >= RIES_TT_W) return 0;
+  unsigned m = (unsigned)T.wge[cls][wlo < 0 ? 0 : wlo] & (unsigned)T.wle[cls][whi >= RIES_TT_W ? RIES_TT_W - 1 : whi];
   unsigned a = (unsigned)atts;
   while (a && m) {
     const int b = RIES_CTZ(a);

@@ -10,6 +10,7 @@
 // reference's streaming decisions exactly.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
 
@@ -666,7 +667,7 @@ struct Search {
     int width = opt.relative_x ? 44 : 40;
     int equ_width = 5;
     int t_width = width + equ_width;
-    int l_pad = opt.solve_for_x ? width / 8 : width / 2;
+    int l_pad = (opt.one_sided || opt.anagram || opt.solve_for_x) ? width / 8 : width / 2; /* ries.c:8113 */
     int r_pad = width - l_pad;
     l_pad -= lf_len; if (l_pad < 0) l_pad = 0;
     r_pad -= rf_len; if (r_pad < 0) r_pad = 0;
@@ -821,13 +822,15 @@ struct Search {
     if (opt.debug_y) out.printf("Will stop after generating searchmax=%g expressions\n", lim_gentotal);
 
     eng.begin(S.P);
+    const bool one_sided = opt.one_sided || opt.anagram; /* ries.c:12319 */
     bool reported_exhaustion = false;
     PassOutput po;
     bool going = true;
     while (going) {
       int using_x;
       int cplx;
-      if (st.lhs_insert > st.rhs_insert) { rmin++; rmax++; using_x = 0; cplx = rmax; }
+      /* --one-sided: 'x' is the sole LHS expression, RHS passes from then on (ries.c:12425) */
+      if ((one_sided && st.lhs_insert >= 1) || (st.lhs_insert > st.rhs_insert)) { rmin++; rmax++; using_x = 0; cplx = rmax; }
       else { lmin++; lmax++; using_x = 1; cplx = lmax; }
       double genf = 0;
       double tf0 = now_sec();
@@ -835,18 +838,34 @@ struct Search {
       po = PassOutput();
       cur_ev = 0;
       double tf1 = now_sec();
-      eng.run_pass(using_x, cplx, forms, best_match, got_exact, po);
       st.forms_seconds += tf1 - tf0;
-      st.engine_seconds += now_sec() - tf1;
-      st.passes++;
-      /* replay the pass's candidates in insertion order with the live threshold */
-      for (size_t k = 0; k < po.events.size(); k++) {
-        cur_ev = &po.events[k];
-        if (cur_ev->kind == EV_EXACT) replay_exact(*cur_ev, using_x);
-        else replay_neighbour(*cur_ev);
+      /* The engine indexes forms with 16 bits.  A pass with more forms (extreme --symbol-weights) is fed in
+         consecutive slices: any split of a pass that keeps insertion order is as good as the whole, since
+         the rows of a pass are all one side and same-side neighbours are never tested (ries.c:8496). */
+      size_t kMaxForms = 60000;
+      if (const char* e = getenv("RIES_FORMS_SLICE")) kMaxForms = (size_t)std::max(1, atoi(e)); /* test hook */
+      for (size_t f0 = 0; f0 < forms.size() || f0 == 0; f0 += kMaxForms) {
+        PassOutput part;
+        double te0 = now_sec();
+        if (forms.size() <= kMaxForms) {
+          eng.run_pass(using_x, cplx, forms, best_match, got_exact, part);
+        } else {
+          std::vector<FormDesc> slice(forms.begin() + f0, forms.begin() + std::min(forms.size(), f0 + kMaxForms));
+          eng.run_pass(using_x, cplx, slice, best_match, got_exact, part);
+        }
+        st.engine_seconds += now_sec() - te0;
+        /* replay the candidates in insertion order with the live threshold */
+        for (size_t k = 0; k < part.events.size(); k++) {
+          cur_ev = &part.events[k];
+          if (cur_ev->kind == EV_EXACT) replay_exact(*cur_ev, using_x);
+          else replay_neighbour(*cur_ev);
+        }
+        cur_ev = 0;
+        resident_rows += part.inserted;
+        po.generated += part.generated; po.dead_ends += part.dead_ends; po.inserted += part.inserted;
+        if (forms.size() <= kMaxForms) break;
       }
-      cur_ev = 0;
-      resident_rows += po.inserted;
+      st.passes++;
       if (using_x) {
         if (opt.debug_y) {
           out.printf("finished LHS from {%d} to {%d}: %g forms expanded, %g expressions.\n", lmin, lmax,
@@ -862,11 +881,12 @@ struct Search {
       }
       st.gen_total += po.generated;
 
-      if ((lmax > S.P.exhaust_cpx) && (rmax > S.P.exhaust_cpx)) { /* 12484 */
+      if ((lmax > S.P.exhaust_cpx) && (one_sided || (rmax > S.P.exhaust_cpx))) { /* 12484 */
         if (num_matches == 0) {
           out.printf("exhaustion timeout (complexity LHS {%d}, RHS {%d}). Possible causes:\n"
                      "  MAX_ELEN %d too small\n", lmax, rmax, RIES_MAX_ELEN);
           if (opt.NOS_options) out.printf("  too many symbols excluded via -N, -O or -S\n");
+          if (opt.anagram) out.printf("  --numeric-anagram too restrictive\n");
           out.printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n");
           reported_exhaustion = true;
         }

@@ -29,7 +29,7 @@ void Sink::printf(const char* fmt, ...) const {
 
 /* init1(): every symbol allowed MAX_ELEN times except W (ries.c:10262-10266) */
 Options::Options() {
-  for (int i = 0; i < 256; i++) sa_alwd[i] = RIES_MAX_ELEN;
+  for (int i = 0; i < 256; i++) { sa_alwd[i] = RIES_MAX_ELEN; preempt_weight[i] = -1; }
   sa_alwd[(unsigned char)'W'] = 0;
 }
 
@@ -192,6 +192,52 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       }
     } else if (strcmp(a, "--no-slow-messages") == 0) {
       o.allow_slow_message = false;
+    } else if (strcmp(a, "--one-sided") == 0) { /* ries.c:11600 */
+      o.one_sided = true;
+    } else if (strcmp(a, "--numeric-anagram") == 0) { /* ries.c:11586, set_anagram 10202 */
+      if (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
+        const char* ana = next_arg();
+        const char* ana_syms = "123456789efprs";
+        for (int k = 0; ana_syms[k]; k++) o.sa_alwd[(unsigned char)ana_syms[k]] = 0;
+        for (int k = 0; ana[k]; k++)
+          if (strchr(ana_syms, ana[k])) o.sa_alwd[(unsigned char)ana[k]]++;
+        o.anagram = true;
+      } else {
+        out.printf("%s: --numeric-anagram should be followed by a string of digits.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--symbol-weights") == 0) { /* ries.c:11689 */
+      if (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
+        while (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
+          const char* arg = next_arg();
+          char tmp[20];
+          strncpy(tmp, arg, 19);
+          tmp[19] = 0;
+          int k = 0;
+          while (tmp[k] == '.' || (tmp[k] >= '0' && tmp[k] <= '9')) k++;
+          if (tmp[k] == ':' && tmp[k + 1]) {
+            tmp[k++] = 0;
+            double w = strtod(tmp, 0);
+            if (w <= 0.0) {
+              out.printf("%s: Symbol weight may not be %f or less.\n", o.argv0.c_str(), 0.0);
+              throw ExitRequest{-1};
+            }
+            if (w > 100.0) w = 100.0;
+            o.preempt_weight[(unsigned char)tmp[k]] = (short)floor(w + 0.5);
+          } else {
+            out.printf("%s: --symbol-weights argument syntax is NUMBER:<sym>, for example\n"
+                       "  12:^   to set weight of '^' to 12\n"
+                       "  Instead I got '%s'\n", o.argv0.c_str(), arg);
+            throw ExitRequest{-1};
+          }
+        }
+      } else {
+        out.printf("%s: --symbol-weights should be followed by one or more tuples\n"
+                   "  of the form NUMBER:<sym>, for example 12:^   to set weight of '^' to 12\n",
+                   o.argv0.c_str());
+        throw ExitRequest{-1};
+      }
     } else if (strcmp(a, "--any-exponents") == 0) {
       o.restrict_exponents = TYPE_NONE;
     } else if (strcmp(a, "--any-subexpressions") == 0) {
@@ -483,7 +529,9 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
     int cls = d.seft - 'a';
     P.sym_char[g] = (unsigned char)d.ch;
     P.sym_cls[g] = (unsigned char)cls;
-    P.sym_wgt[g] = (short)(d.weight + 10);
+    /* base complexity 10 + per-symbol weight, unless --symbol-weights overrides it (ries.c:9872) */
+    P.sym_wgt[g] = (o.preempt_weight[(unsigned char)d.ch] >= 0) ? o.preempt_weight[(unsigned char)d.ch]
+                                                                  : (short)(d.weight + 10);
     P.sym_alwd[g] = o.sa_alwd[(unsigned char)d.ch];
     P.sym_amkey[g] = amkey_of(d.ch);
     P.sym_mask[g] = 0;

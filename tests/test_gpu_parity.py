@@ -96,9 +96,11 @@ def test_gpu_node_arena_regrow(product_lib):
 @pytest.mark.parametrize("env_extra", [{"RIES_NO_SMALL_POST": "1"}, {"RIES_FORCE_SMALL_POST": "1"},
                                        {"RIES_NO_GRAPHS": "1"},
                                        {"RIES_FAKE_SHARD": "3", "RIES_SHARD_MIN": "0"},
-                                       {"RIES_FAKE_SHARD": "2", "RIES_SHARD_MIN": "2000", "RIES_ARENA_CAP": "4096"}],
+                                       {"RIES_FAKE_SHARD": "2", "RIES_SHARD_MIN": "2000", "RIES_ARENA_CAP": "4096"},
+                                       {"RIES_FORMS_SLICE": "7"}],
                          ids=["general-kernels-only", "mispredicted-small-pass", "no-graphs",
-                              "every-pass-sharded-3-virtual-ranks", "large-passes-sharded-2-virtual-ranks-regrow"])
+                              "every-pass-sharded-3-virtual-ranks", "large-passes-sharded-2-virtual-ranks-regrow",
+                              "passes-fed-in-slices-of-7-forms"])
 def test_gpu_pass_variants_agree(product_lib, env_extra):
     """Small passes run through a fused single-block kernel, the rest through the general kernels, a wrong
     size prediction is rerun, and K1 can be sharded over (virtual) ranks with the complete expressions
