@@ -418,6 +418,19 @@ def main():
 
     if sharded_extra is not None:
         line["sharded_search"] = sharded_extra
+    if world == 1:
+        # SURVEY 8(d) also defines time-to-full-report from PROCESS start: the `ries` binary in a fresh process
+        # (CUDA context creation, cold allocations, search, teardown) -- what a command-line user sees; the
+        # step time above is a warm call on a live engine, what the web worker's reused module sees
+        exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
+        if os.path.exists(exe):
+            cold = []
+            for _ in range(2):
+                tc0 = time.perf_counter()
+                subprocess.run([exe, args.target, "-l" + args.level, "-F3", "--no-slow-messages"],
+                               capture_output=True, env=dict(os.environ, RIES_DEVICE=str(local_rank)))
+                cold.append(time.perf_counter() - tc0)
+            line["time_to_full_report_cold_process_s"] = min(cold)
     if not args.no_cpu_baseline and world == 1:
         binary, kind = ref_binary()
         if binary:

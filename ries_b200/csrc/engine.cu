@@ -1516,6 +1516,14 @@ class DeviceEngine : public Engine {
     h2d_bytes += nforms * sizeof(FormDesc) + sizeof(PassArgs);
 
     bool no_small_post = !use_small_post_;
+    {
+      /* sizes grow ~1.3-1.6x per complexity step: keep twice the previous same-side pass in hand, so that
+         the overflow-and-rerun path stays the exception (it costs a whole pass) */
+      const int side = using_x ? 1 : 0;
+      const size_t want_nodes = (size_t)prev_nodes_[side] * 2, want_done = (size_t)prev_done_[side] * 2;
+      if (!getenv("RIES_ARENA_CAP") && (want_nodes > nodes_.cap || want_done > done_.cap))
+        grow_arena(std::max(want_nodes, nodes_.cap), std::max(want_done, done_.cap));
+    }
     while (true) {
       /* the merged table needs room for every survivor the arena can hold */
       ensure_table((size_t)nt_ + done_.cap);
