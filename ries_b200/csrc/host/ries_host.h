@@ -61,6 +61,7 @@ struct Options {
   bool allow_slow_message = true;
   bool no_cv_simplify = false;
   bool solve_for_x = false; /* -s / --try-solve-for-x (ries.c:11756) */
+  bool refinement = true;   /* --no-refinement (11577): the threshold never shrinks; every match inside it is printed once */
   bool one_sided = false;   /* --one-sided (11600): 'x' is the only LHS, RHS passes from then on (12425) */
   bool anagram = false;     /* --numeric-anagram (11586): digit budget through sa_alwd, implies one_sided */
   short preempt_weight[256]; /* --symbol-weights (11689): -1 = the built-in weight */

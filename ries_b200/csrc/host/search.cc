@@ -419,6 +419,39 @@ struct Search {
     return o;
   }
 
+  /* --no-refinement bookkeeping (ries.c:10697-10738, 7848-7873, 7919-7942): the list of reported equations
+     as one symbol string " lhs=rhs lhs=rhs ...", searched by substring; the reported deltas; and what both
+     add to the reference's memory counters. */
+  std::string nr_matches;
+  size_t nr_alloc = 0;
+  std::vector<double> nr_deltas;
+  long nr_kib = 0;
+  unsigned long nr_bytes = 0;
+  void nr_init() {
+    if (opt.refinement) return;
+    nr_deltas.assign((size_t)opt.max_matches + 1, 0.0);
+    size_t space = ((size_t)opt.max_matches) * (size_t)(RIES_MAX_ELEN + 1);
+    nr_alloc = space;
+    if (opt.solve_for_x) nr_alloc += space;
+    if (opt.out_format == OF_CONDENSED || opt.out_format == OF_NORMAL) nr_alloc += space * 4;
+    nr_matches = " ";
+    nr_kib = (long)(nr_alloc >> 10);
+    nr_bytes = 2;
+  }
+  bool unique_eqn(const std::string& lhs, const std::string& rhs, bool addit) { /* ries.c:7848 */
+    const size_t TS_ALLOC_R = (RIES_MAX_ELEN + 1) * 4;
+    std::string te = " " + lhs + "=" + rhs + " ";
+    if (te.size() > TS_ALLOC_R - 1) te.resize(TS_ALLOC_R - 1); /* symstrncat truncates */
+    if (nr_matches.find(te) != std::string::npos) return false;
+    if (addit) {
+      std::string add = te.substr(1);
+      size_t room = (nr_alloc > nr_matches.size() + 1) ? nr_alloc - 1 - nr_matches.size() : 0;
+      nr_matches += add.substr(0, std::min(room, add.size()));
+      nr_bytes += (unsigned long)(add.size() + 1);
+    }
+    return true;
+  }
+
   /* Memory the reference's allocator would report for `nodes` tree nodes: sizeof(expr) = 72 on
      LP64 (ries.c:2955), 64 KiB blocks with an 8-byte back link (my_alloc 4837-4900). */
   static void ref_memory(long nodes, long* kib, unsigned long* bytes) {
@@ -456,6 +489,7 @@ struct Search {
       out.printf("           distinct: %11ld  %11ld  %11ld", st.lhs_insert, st.rhs_insert, total_insert);
       long kib; unsigned long bytes;
       ref_memory(live_rows(), &kib, &bytes);
+      kib += nr_kib; bytes += nr_bytes;
       if (kib > 1024L) out.printf("  Memory: %ldKiB\n", kib);
       else out.printf("  Memory: %ld B\n", bytes);
       out.printf("\n");
@@ -646,20 +680,37 @@ struct Search {
   /* report_match ries.c:7887 */
   void report_match(const std::string& le_in, const std::string& re_in, double root, double delta) {
     if ((delta == 0.0) && got_exact) return;
+    if (!opt.refinement) { /* prune on the delta, then on the equation itself (7919-7953) */
+      size_t i = 0;
+      for (; i < (size_t)num_matches; i++)
+        if (nr_deltas[i] == delta) return;
+      if (i < nr_deltas.size()) nr_deltas[i] = delta;
+      nr_bytes += sizeof(double);
+      if (!unique_eqn(le_in, re_in, true)) return;
+    }
     std::string le = le_in, re = re_in;
-    if (opt.solve_for_x) try_solve(le, re);
+    if (opt.solve_for_x) {
+      try_solve(le, re);
+      if (!opt.refinement && !unique_eqn(le, re, true)) return; /* 8013 */
+    }
     std::string l_fmt, r_fmt;
     if (opt.out_format == OF_POSTFIX) {
       l_fmt = le; r_fmt = re;
     } else if (opt.out_format == OF_CONDENSED || opt.out_format == OF_NORMAL) {
+      std::string cond[2];
+      bool okk[2];
       for (int side = 0; side < 2; side++) {
-        std::string pre = infix_preproc(icx, side ? re : le), term;
+        std::string pre = infix_preproc(icx, side ? re : le);
         unsigned char top;
-        bool ok = infix_1(icx, pre, term, top);
-        if (!ok) term.clear();
-        else if (opt.out_format == OF_NORMAL) term = infix_expand(icx, term);
-        (side ? r_fmt : l_fmt) = term;
+        okk[side] = infix_1(icx, pre, cond[side], top);
+        if (side == 0) { /* the LHS is finished (expanded) before the RHS is started (8033-8047) */
+          if (!okk[0]) l_fmt.clear();
+          else l_fmt = (opt.out_format == OF_NORMAL) ? infix_expand(icx, cond[0]) : cond[0];
+        }
       }
+      if (!opt.refinement && !unique_eqn(cond[0], cond[1], true)) return; /* 8062 */
+      if (!okk[1]) r_fmt.clear();
+      else r_fmt = (opt.out_format == OF_NORMAL) ? infix_expand(icx, cond[1]) : cond[1];
     } else {
       l_fmt = postfix_formatter(le); r_fmt = postfix_formatter(re);
     }
@@ -763,6 +814,7 @@ struct Search {
     double score = fabs(delta);
     if ((best_match > 0) && (score > best_match)) return;
     if (score < opt.min_matchsize) return;
+    if (!opt.refinement && !unique_eqn(sym_chars(ev.lhs.sym), sym_chars(ev.rhs.sym), false)) return; /* 8611 */
     report_match(sym_chars(ev.lhs.sym), sym_chars(ev.rhs.sym), S.P.target, 0.0);
   }
 
@@ -776,6 +828,7 @@ struct Search {
     double delta = (ev.rhs.val - ev.lhs.val) / total_deriv;
     double score = fabs(delta);
     if ((score > best_match) || (score < opt.min_matchsize)) return;
+    if (!opt.refinement && !unique_eqn(sym_chars(ev.lhs.sym), sym_chars(ev.rhs.sym), false)) return; /* 8280 */
     if (ev.newton_err) return;
     delta = ev.root - S.P.target;
     score = fabs(delta);
@@ -785,7 +838,7 @@ struct Search {
       return;
     } else if (score < best_match) {
       report_match(le, re, ev.root, delta);
-      best_match = (score * 0.999) - S.k_min_best_match;
+      if (opt.refinement) best_match = (score * 0.999) - S.k_min_best_match; /* 8351 */
       check_exit(false);
     }
   }
@@ -802,6 +855,7 @@ struct Search {
     finish_setup(opt, S, out);
     icx.S = &S;
     best_match = S.init_match_dist;
+    nr_init();
 
     /* header ries.c:12327-12337 */
     {

@@ -192,6 +192,8 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       }
     } else if (strcmp(a, "--no-slow-messages") == 0) {
       o.allow_slow_message = false;
+    } else if (strcmp(a, "--no-refinement") == 0) { /* ries.c:11577 */
+      o.refinement = false;
     } else if (strcmp(a, "--one-sided") == 0) { /* ries.c:11600 */
       o.one_sided = true;
     } else if (strcmp(a, "--numeric-anagram") == 0) { /* ries.c:11586, set_anagram 10202 */
