@@ -4,8 +4,8 @@
 //                           [ge_2 + exec, ries.c:8908-9475, 5308-5950]
 //   K2  k_reorder/k_rs_onesweep       stable LSD radix sort of the pass's survivors on the fp64 value
 //       k_classify_compact  duplicate pruning inside the pass and against the resident table
-//       k_merge_new/old     merge into the resident sorted table         [bt_insert, ries.c:8622-8724]
-//   K3  k_match             gap-local neighbour test with the derivative-scaled window
+//       k_match_merge_new, k_merge_old   merge into the resident sorted table   [bt_insert, ries.c:8622-8724]
+//   K3  k_match_merge_new   gap-local neighbour test with the derivative-scaled window
 //                                                           [check_sides/check_match, 8488, 8243]
 //   K4  k_refine            cv_simplify + Newton on the compacted candidates        [7297, 7139]
 //
@@ -958,21 +958,27 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   }
 }
 
-/* K3.  A new row's predecessor AT ITS INSERTION TIME is the old-table row below its gap unless a
-   same-pass row with a smaller sequence number already sits between them (that one is same-side, so
-   no test happens: check_sides, ries.c:8496-8538).  Likewise for the successor. */
-__global__ void k_match(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+/* K3 + merge of the new rows.  A new row's predecessor AT ITS INSERTION TIME is the old-table row below
+   its gap unless a same-pass row with a smaller sequence number already sits between them (that one is
+   same-side, so no test happens: check_sides, ries.c:8496-8538).  Likewise for the successor.  The row is
+   read once: it goes to its place in the merged table and into the neighbour tests. */
+__global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
   if (!pass_ok(C)) return;
   const u32 nu = C->n_uniq;
   const DevPtrs D = *Dp;
   const u32 nt = T->nt;
   const Row* __restrict__ trow = D.trow[T->cur];
+  Row* mrow = D.trow[T->cur ^ 1];
+  double* mval = D.tval[T->cur ^ 1];
   const u32* __restrict__ uniq_seq = D.uniq_seq;
   const u32* __restrict__ uniq_gap = D.uniq_gap;
   const int using_x = A->using_x;
   const double best_match0 = A->best_match0;
   for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
     const u32 s = uniq_seq[u], g = uniq_gap[u];
+    const Row f = D.surv[s];
+    mrow[u + g] = f;
+    mval[u + g] = f.val;
     bool test_prev = g > 0, test_next = g < nt;
     if (test_prev) {
       for (u32 j = u; j-- > 0 && uniq_gap[j] == g;)
@@ -982,8 +988,6 @@ __global__ void k_match(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const 
       for (u32 j = u + 1; j < nu && uniq_gap[j] == g; j++)
         if (uniq_seq[j] < s) { test_next = false; break; }
     }
-    if (!test_prev && !test_next) continue;
-    const Row f = D.surv[s];
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !test_prev : !test_next) continue;
       const Row o = trow[side == 0 ? g - 1 : g];
@@ -996,20 +1000,6 @@ __global__ void k_match(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const 
       if (score > best_match0) continue; /* NaN passes, as in the reference's test (8270) */
       push_event(D.events, A->cap_events, C, s, side == 0 ? EV_PREV : EV_NEXT, L, R);
     }
-  }
-}
-
-__global__ void k_merge_new(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
-  if (C->overflow) return;
-  const u32 nu = C->n_uniq;
-  const DevPtrs D = *Dp;
-  Row* mrow = D.trow[T->cur ^ 1];
-  double* mval = D.tval[T->cur ^ 1];
-  for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
-    Row r = D.surv[D.uniq_seq[u]];
-    u32 pos = u + D.uniq_gap[u];
-    mrow[pos] = r;
-    mval[pos] = r.val;
   }
 }
 
@@ -1693,8 +1683,7 @@ class DeviceEngine : public Engine {
           break;
         }
         k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-        k_match<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-        k_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+        k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_merge_old<<<small ? 48u : wide_grid_, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
         break;
       default:
@@ -1737,7 +1726,7 @@ class DeviceEngine : public Engine {
       CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
       const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1
                                  : (stage == 1) ? ((small == 2) ? 1 : 11)
-                                 : (stage == 2) ? ((small == 2) ? 1 : 4) : 2;
+                                 : (stage == 2) ? ((small == 2) ? 1 : 3) : 2;
       kernel_launches += k;
       stage_launches[stage] += k;
     }
