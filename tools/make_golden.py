@@ -2,7 +2,8 @@
 """Generates tests/golden/*.txt by running the UNMODIFIED reference (oracle/_ref/ries = gcc -O2 of
 /root/reference/public/ries.c, stock glibc) on every case of tests/golden/cases.json.  The reference
 cannot travel to the GPU box, so its outputs are committed as fixtures.  `Time:` is normalised.
-usage: tools/make_golden.py [--big]   (--big also regenerates the minutes-long -l5/-l6 cases)"""
+usage: tools/make_golden.py [--big] [--huge]   (--big also regenerates the minutes-long -l5/-l6 cases,
+--huge the -l7 one: 47 minutes of one host core)"""
 import json, os, re, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -12,6 +13,8 @@ big = "--big" in sys.argv
 env = dict(os.environ, HOME="/nonexistent")
 for c in cases:
     if c.get("big") and not big:
+        continue
+    if c.get("huge") and "--huge" not in sys.argv:
         continue
     r = subprocess.run([REF] + c["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
     text = re.sub(r"Time: [0-9.]+", "Time: X", r.stdout).replace(REF, "ries")
