@@ -90,6 +90,8 @@ struct PassCtl {
   u32 nt_before;          /* table rows before this pass */
   u32 pad;
   u64 dead;               /* dead-ends of the pass */
+  u32 aux_ticket;         /* k_local_filter / k_compact_kept (sharded passes) */
+  u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
 };
 
 #define HEAD_EVENTS 16 /* candidates copied back together with the counters (one copy, one sync per pass) */
@@ -122,6 +124,10 @@ struct DevPtrs {
   Row* gdone;           /* all ranks' complete expressions, rank-major (sharded passes only) */
   uint16_t* gdone_form;
   Row* surv;
+  uint16_t* surv_form; /* form index of surv[i] (sharded passes: needed again after the exchange) */
+  unsigned char* keep; /* sharded passes: surv[i] takes part in the exchange */
+  Row* ksend;          /* ... compacted rows / forms this rank sends */
+  uint16_t* ksend_form;
   u64* keys[2];
   u32* idx[2];
   u32* form_first;
@@ -162,7 +168,7 @@ __global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, Ta
   if (threadIdx.x == 0) {
     C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
     C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
-    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0;
+    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0;
     u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
     if (e == 0) e = 16;
     T->epoch = e;
@@ -584,6 +590,7 @@ k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
     u32 pos = D.form_base[f] + (i - D.form_first[f]);
     Row r = done[i];
     D.surv[pos] = r;
+    D.surv_form[pos] = f;
     const u64 k = key_of(r.val);
     D.keys[0][pos] = k;
     D.idx[0][pos] = pos;
@@ -1239,6 +1246,145 @@ k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState*
   }
 }
 
+/* ------------------------------------------------ sharded passes: local pre-dedupe -------- */
+/* One search over several GPUs: before the ranks exchange their complete expressions, each drops the ones
+   that cannot matter, using its replica of the table and its own survivors in sorted order:
+     value already in the table on the SAME side      -> dropped (check_exact_match discards it, 8550-8593)
+     value already in the table on the opposite side  -> kept, every occurrence (each is an EXACT event)
+     new value                                        -> only the first occurrence in insertion order is kept
+   The global first-inserted winner of a value is the minimum over the ranks' first occurrences, so the
+   replicated dedupe that follows sees exactly the rows it needs, in the same relative order. */
+__global__ void __launch_bounds__(CC_THREADS)
+k_local_filter(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+  __shared__ double s_win[CC_WIN + 1];
+  __shared__ u32 s_lo, s_hi;
+  if (!pass_ok(C)) return;
+  const u32 n = C->done_count;
+  const u32 nchunks = (n + CC_CHUNK - 1) / CC_CHUNK;
+  const DevPtrs D = *Dp;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 cur = T->cur, nt = T->nt;
+  const double* __restrict__ tval = D.tval[cur];
+  const Row* __restrict__ trow = D.trow[cur];
+  const u64* __restrict__ keys = D.keys[0];
+  const u32* __restrict__ idx = D.idx[0];
+  const int using_x = A->using_x;
+  for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const u32 base = chunk * CC_CHUNK;
+    const u32 last = min(base + CC_CHUNK, n) - 1;
+    if (warp == 0) {
+      u32 r = warp_lower_bound(tval, nt, val_of_key(keys[base]));
+      if (lane == 0) s_lo = r;
+    } else if (warp == 1) {
+      u32 r = warp_lower_bound(tval, nt, val_of_key(keys[last]));
+      if (lane == 0) s_hi = r;
+    }
+    __syncthreads();
+    const u32 lo = s_lo, hi = s_hi;
+    const u32 wn = hi - lo;
+    const u32 wload = min(hi + 1, nt) - lo;
+    const bool in_smem = wn <= CC_WIN;
+    if (in_smem)
+      for (u32 j = tid; j < wload; j += CC_THREADS) s_win[j] = tval[lo + j];
+    __syncthreads();
+    const double* win = in_smem ? s_win : tval + lo;
+#pragma unroll
+    for (int r = 0; r < CC_ITEMS; r++) {
+      const u32 i = base + r * CC_THREADS + tid;
+      if (i < n) {
+        const u64 k = keys[i];
+        const double v = val_of_key(k);
+        const bool dup_prev = (i > 0) && (keys[i - 1] == k);
+        u32 a = 0, b = wn;
+        while (a < b) {
+          u32 mid = (a + b) >> 1;
+          if (win[mid] < v) a = mid + 1; else b = mid;
+        }
+        const u32 p = lo + a;
+        bool kp;
+        if ((p < nt) && (win[a] == v)) {
+          const bool tree_is_lhs = (trow[p].der != 0.0);
+          kp = using_x ? !tree_is_lhs : tree_is_lhs;
+        } else {
+          kp = !dup_prev;
+        }
+        D.keep[idx[i]] = kp ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+/* Kept rows, compacted in insertion order (chunks by ticket, look-back over the chunk counts). */
+__global__ void __launch_bounds__(256)
+k_compact_kept(const DevPtrs* Dp, PassCtl* C, const TableState* T) {
+  __shared__ u32 s_warp[8];
+  __shared__ u32 s_chunk, s_base;
+  if (!pass_ok(C)) return;
+  const u32 n = C->done_count;
+  const u32 nchunks = (n + 255) / 256;
+  if (blockIdx.x >= nchunks) return;
+  const DevPtrs D = *Dp;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  volatile u64* state = (volatile u64*)D.cc_state;
+  const u64 epoch = (u64)(T->epoch + 9u);
+  while (true) {
+    if (tid == 0) s_chunk = atomicAdd(&C->aux_ticket, 1u);
+    __syncthreads();
+    const u32 chunk = s_chunk;
+    if (chunk >= nchunks) break;
+    const u32 i = chunk * 256 + tid;
+    const bool fl = (i < n) && D.keep[i];
+    const u32 b = __ballot_sync(0xffffffffu, fl);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    u32 woff = 0, total = 0;
+    for (u32 w = 0; w < 8; w++) { u32 c = s_warp[w]; if (w < warp) woff += c; total += c; }
+    if (tid == 0) {
+      const u64 tag = epoch << 34;
+      u32 ex = 0;
+      if (chunk == 0) {
+        state[0] = tag | (RS_FLAG_INC << 32) | total;
+      } else {
+        state[chunk] = tag | (RS_FLAG_AGG << 32) | total;
+        int c = (int)chunk - 1;
+        while (c >= 0) {
+          u64 w;
+          do { w = state[c]; } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
+          ex += (u32)w;
+          if (((w >> 32) & 3ull) == RS_FLAG_INC) break;
+          c--;
+        }
+        state[chunk] = tag | (RS_FLAG_INC << 32) | (u64)(ex + total);
+      }
+      s_base = ex;
+      if (chunk == nchunks - 1) C->n_kept = ex + total;
+    }
+    __syncthreads();
+    if (fl) {
+      const u32 u = s_base + woff + __popc(b & ((1u << lane) - 1));
+      D.ksend[u] = D.surv[i];
+      D.ksend_form[u] = D.surv_form[i];
+    }
+    __syncthreads();
+  }
+}
+
+/* Between the local regroup+sort of a sharded pass and the replicated one: fresh look-back tags, zeroed
+   form tables, histograms and tickets. */
+__global__ void k_stage1_reset(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+  const u32 nforms = (u32)A->nforms;
+  for (u32 i = threadIdx.x; i < nforms; i += blockDim.x) { D->form_first[i] = 0; D->form_cnt[i] = 0; }
+  u32* sc = (u32*)D->sortctl;
+  for (u32 i = threadIdx.x; i < sizeof(SortCtl) / 4; i += blockDim.x) sc[i] = 0;
+  if (threadIdx.x == 0) {
+    C->chunk_ticket = 0; C->aux_ticket = 0;
+    u32 e = (T->epoch + 16) & 0x3ffffff0u;
+    if (e == 0) e = 16;
+    T->epoch = e;
+  }
+}
+
 /* Upper bound by a whole warp over a sorted u32 array: #{u : a[u] <= key}. */
 __device__ __forceinline__ u32 warp_upper_bound_u32(const u32* __restrict__ a, u32 n, u32 key) {
   const u32 lane = threadIdx.x & 31;
@@ -1441,6 +1587,7 @@ class DeviceEngine : public Engine {
     for (int i = 0; i < 3; i++) form_[i].release(st_);
     uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); tiles_.release(st_); staged_.release(st_);
     rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_); allctl_.release(st_);
+    surv_form_.release(st_); keep_.release(st_); ksend_.release(st_); ksend_form_.release(st_);
     cudaStreamSynchronize(st_);
     cudaFreeHost(h_allctl_);
     cudaFree(d_P_); cudaFree(d_tt_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
@@ -1506,6 +1653,8 @@ class DeviceEngine : public Engine {
     h2d_bytes += nforms * sizeof(FormDesc) + sizeof(PassArgs);
 
     bool no_small_post = !use_small_post_;
+    unsigned long long gen_k1 = 0; /* sharded passes: complete expressions of all ranks' K1, before the pre-dedupe */
+    bool was_sharded = false;
     {
       /* sizes grow ~1.3-1.6x per complexity step: keep twice the previous same-side pass in hand, so that
          the overflow-and-rerun path stays the exception (it costs a whole pass) */
@@ -1532,8 +1681,10 @@ class DeviceEngine : public Engine {
       const int shard_world = ds.fake_world > 1 ? ds.fake_world : ds.world;
       const bool shard = shard_world > 1 && prev_done_[using_x ? 1 : 0] >= shard_min_;
       h_args_->shard_rank = (shard && ds.fake_world <= 1) ? ds.rank : 0;
-      h_args_->shard_world = shard ? shard_world : 1; h_args_->gathered = shard ? 1 : 0;
+      h_args_->shard_world = shard ? shard_world : 1;
+      h_args_->gathered = 0; /* a sharded pass switches to the gathered arrays after the exchange */
       h_args_->pad2 = 0;
+      if (shard && small == 2) small = 1; /* the single-block kernel has no local/global split */
       CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                  cudaMemcpyHostToDevice, st_));
       if (!shard) {
@@ -1545,13 +1696,14 @@ class DeviceEngine : public Engine {
         collect_stage_times(0, 3);
       } else {
         size_t want_nodes = nodes_.cap, want_done = done_.cap;
-        const u32 fovf = sharded_front(max_len, small, &want_nodes, &want_done);
+        const u32 fovf = sharded_front(max_len, small, &want_nodes, &want_done, &gen_k1);
         if (fovf) {
           grow_arena(std::max(want_nodes, nodes_.cap * ((fovf & OVF_NODES) ? 2 : 1)),
                      std::max(want_done, done_.cap * ((fovf & OVF_DONE) ? 2 : 1)));
           continue;
         }
         sharded_passes++;
+        was_sharded = true;
         launch_stages(1, 3, max_len, small);
         CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -1579,11 +1731,12 @@ class DeviceEngine : public Engine {
       fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
               using_x ? "LHS" : "RHS", cplx, nforms, max_len, h_ctl_->node_count, n, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
     }
+    const unsigned long long gen = was_sharded ? gen_k1 : (unsigned long long)n;
     prev_nodes_[using_x ? 1 : 0] = h_ctl_->node_count;
-    prev_done_[using_x ? 1 : 0] = n;
+    prev_done_[using_x ? 1 : 0] = (u32)std::min<unsigned long long>(gen, 0xffffffffull);
     expand_nodes += h_ctl_->node_count;
     sort_keys += n;
-    out.generated = (double)n;
+    out.generated = (double)gen;
     out.dead_ends = (double)h_ctl_->dead;
     out.inserted = (long)nu;
     last_nu_ = nu;
@@ -1693,17 +1846,20 @@ class DeviceEngine : public Engine {
     }
   }
 
+  /* mirrors what k_pass_begin / k_stage1_reset do to TableState::epoch */
+  void bump_epoch() {
+    epoch_host_ = (epoch_host_ + 16) & 0x3ffffff0u;
+    if (epoch_host_ == 0) {
+      /* 2^26 bumps later the tags wrap: clear the look-back state so old tags cannot alias new ones */
+      epoch_host_ = 16;
+      CUDA_CHECK(cudaMemsetAsync(rs_state_.p, 0, rs_state_.cap * sizeof(u64), st_));
+      CUDA_CHECK(cudaMemsetAsync(cc_state_.p, 0, cc_state_.cap * sizeof(u64), st_));
+    }
+  }
+
   /* Stages [first, last] of a pass on the stream; ev_[k] is recorded before stage k (and after the last). */
   void launch_stages(int first, int last, int max_len, int small) {
-    if (first == 0) {
-      epoch_host_ = (epoch_host_ + 16) & 0x3ffffff0u; /* what k_pass_begin does to TableState::epoch */
-      if (epoch_host_ == 0) {
-        /* 2^26 passes later the tags wrap: clear the look-back state so old tags cannot alias new ones */
-        epoch_host_ = 16;
-        CUDA_CHECK(cudaMemsetAsync(rs_state_.p, 0, rs_state_.cap * sizeof(u64), st_));
-        CUDA_CHECK(cudaMemsetAsync(cc_state_.p, 0, cc_state_.cap * sizeof(u64), st_));
-      }
-    }
+    if (first == 0) bump_epoch();
     CUDA_CHECK(cudaEventRecord(ev_[first], st_));
     for (int stage = first; stage <= last; stage++) {
       if (!use_graphs_) {
@@ -1740,15 +1896,32 @@ class DeviceEngine : public Engine {
     (void)cudaGetLastError();
   }
 
-  /* K1 of a pass sharded over `world` ranks (or virtual ranks), then the all-gather of the complete
-     expressions into gdone/gdone_form in rank-major order and the totals into the device control block.
-     Returns the overflow flags (any rank's); on overflow nothing was gathered and *want_* hold the sizes to
-     grow to.  Every rank computes the same totals, so every rank takes the same decisions afterwards. */
-  u32 sharded_front(int max_len, int small, size_t* want_nodes, size_t* want_done) {
+  /* Front half of a pass sharded over `world` ranks (or virtual ranks): K1 on this rank's forms, the local
+     regroup + sort + pre-dedupe (k_local_filter), then the all-gather of what is left into
+     gdone/gdone_form in rank-major order and the totals into the device control block.  Returns the
+     overflow flags (any rank's); on overflow nothing was gathered and *want_* hold the sizes to grow to.
+     Every rank computes the same totals, so every rank takes the same decisions afterwards. */
+  u32 sharded_front(int max_len, int small, size_t* want_nodes, size_t* want_done, unsigned long long* gen_k1) {
     const DistState& ds = dist_state();
     const bool fake = ds.fake_world > 1;
     const int world = fake ? ds.fake_world : ds.world;
     std::vector<PassCtl> all((size_t)world);
+    bool ch = false;
+    ch |= keep_.ensure(done_.cap, st_);
+    ch |= ksend_.ensure(done_.cap, st_);
+    ch |= ksend_form_.ensure(done_.cap, st_);
+    if (ch) { ptrs_dirty_ = true; upload_ptrs(); }
+    const u32 g_wide = small ? 12u : wide_grid_;
+    /* K1 -> regroup + sort of this rank's own expressions -> drop what cannot matter -> compact */
+    auto local_front = [&]() {
+      launch_stages(0, 1, max_len, small);
+      k_local_filter<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+      k_compact_kept<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+      bump_epoch();
+      k_stage1_reset<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+      kernel_launches += 3;
+      stage_launches[1] += 3;
+    };
     if (fake) {
       /* test hook: the virtual ranks run one after the other on this GPU; the "all-gather" is a copy */
       size_t off = 0;
@@ -1756,20 +1929,20 @@ class DeviceEngine : public Engine {
       for (int r = 0; r < world; r++) {
         h_args_->shard_rank = r;
         CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET, cudaMemcpyHostToDevice, st_));
-        launch_stages(0, 0, max_len, small);
+        local_front();
         CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
-        collect_stage_times(0, 0);
+        collect_stage_times(0, 1);
         all[r] = *h_ctl_;
         ovf |= h_ctl_->overflow;
         if (h_ctl_->overflow) break;
-        const size_t c = h_ctl_->done_count;
+        const size_t c = h_ctl_->n_kept;
         if (off + c > done_.cap) { ovf |= OVF_DONE; *want_done = std::max(*want_done, (off + c) * 2); break; }
         if (gdone_.ensure(off + c, st_, true)) ptrs_dirty_ = true;
         if (gdone_form_.ensure(off + c, st_, true)) ptrs_dirty_ = true;
         if (c) {
-          CUDA_CHECK(cudaMemcpyAsync(gdone_.p + off, done_.p, c * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
-          CUDA_CHECK(cudaMemcpyAsync(gdone_form_.p + off, done_form_.p, c * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
+          CUDA_CHECK(cudaMemcpyAsync(gdone_.p + off, ksend_.p, c * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
+          CUDA_CHECK(cudaMemcpyAsync(gdone_form_.p + off, ksend_form_.p, c * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
         }
         off += c;
       }
@@ -1781,19 +1954,19 @@ class DeviceEngine : public Engine {
         return ovf;
       }
     } else {
-      launch_stages(0, 0, max_len, small);
+      local_front();
       allctl_.ensure((size_t)world, st_); /* not in the pointer table */
       dist_allgather(d_ctl_, allctl_.p, sizeof(PassCtl), st_);
       CUDA_CHECK(cudaMemcpyAsync(h_allctl_, allctl_.p, (size_t)world * sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
       CUDA_CHECK(cudaStreamSynchronize(st_));
-      collect_stage_times(0, 0);
+      collect_stage_times(0, 1);
       d2h_bytes += (size_t)world * sizeof(PassCtl);
       u32 ovf = 0;
       size_t total = 0;
       for (int r = 0; r < world; r++) {
         all[r] = h_allctl_[r];
         ovf |= all[r].overflow;
-        total += all[r].done_count;
+        total += all[r].n_kept;
         if (all[r].overflow & OVF_NODES) *want_nodes = std::max(*want_nodes, (size_t)all[r].node_count * 2);
         if (all[r].overflow & OVF_DONE) *want_done = std::max(*want_done, (size_t)all[r].done_count * 2);
       }
@@ -1803,23 +1976,27 @@ class DeviceEngine : public Engine {
       if (gdone_form_.ensure(total, st_)) ptrs_dirty_ = true;
       std::vector<size_t> bytes((size_t)world), offs((size_t)world);
       size_t off = 0;
-      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].done_count * sizeof(Row); offs[r] = off * sizeof(Row); off += all[r].done_count; }
-      dist_allgatherv(done_.p, gdone_.p, bytes.data(), offs.data(), st_);
+      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].n_kept * sizeof(Row); offs[r] = off * sizeof(Row); off += all[r].n_kept; }
+      dist_allgatherv(ksend_.p, gdone_.p, bytes.data(), offs.data(), st_);
       off = 0;
-      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].done_count * sizeof(uint16_t); offs[r] = off * sizeof(uint16_t); off += all[r].done_count; }
-      dist_allgatherv(done_form_.p, gdone_form_.p, bytes.data(), offs.data(), st_);
+      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].n_kept * sizeof(uint16_t); offs[r] = off * sizeof(uint16_t); off += all[r].n_kept; }
+      dist_allgatherv(ksend_form_.p, gdone_form_.p, bytes.data(), offs.data(), st_);
       gather_bytes += total * (sizeof(Row) + sizeof(uint16_t));
     }
-    /* totals into the device control block, as if one K1 had produced everything */
+    /* totals into the device control block, as if one K1 had produced exactly the kept expressions; from
+       here on the regroup kernels read the gathered arrays */
     PassCtl t = all[0];
-    unsigned long long nodes = 0, done = 0, dead = 0;
-    for (int r = 0; r < world; r++) { nodes += all[r].node_count; done += all[r].done_count; dead += all[r].dead; }
+    unsigned long long nodes = 0, done = 0, kept = 0, dead = 0;
+    for (int r = 0; r < world; r++) { nodes += all[r].node_count; done += all[r].done_count; kept += all[r].n_kept; dead += all[r].dead; }
     t.node_count = (u32)std::min<unsigned long long>(nodes, 0xffffffffull);
-    t.done_count = (u32)done;
+    t.done_count = (u32)kept;
     t.dead = dead;
-    t.lvl_begin = t.lvl_end = 0; t.tile_ticket = 0; t.blocks_done = 0;
+    t.lvl_begin = t.lvl_end = 0; t.tile_ticket = 0; t.blocks_done = 0; t.chunk_ticket = 0; t.aux_ticket = 0;
+    *gen_k1 = done;
     *h_ctl_ = t;
     CUDA_CHECK(cudaMemcpyAsync(d_ctl_, h_ctl_, sizeof(PassCtl), cudaMemcpyHostToDevice, st_));
+    h_args_->gathered = 1;
+    CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET, cudaMemcpyHostToDevice, st_));
     if (ptrs_dirty_) upload_ptrs();
     return 0;
   }
@@ -1831,13 +2008,14 @@ class DeviceEngine : public Engine {
     ch |= done_.ensure(want_done, st_);
     ch |= done_form_.ensure(done_.cap, st_);
     ch |= surv_.ensure(done_.cap, st_);
+    ch |= surv_form_.ensure(done_.cap, st_);
     for (int b = 0; b < 2; b++) { ch |= keys_[b].ensure(done_.cap, st_); ch |= idx_[b].ensure(done_.cap, st_); }
     ch |= uniq_seq_.ensure(done_.cap, st_);
     ch |= uniq_gap_.ensure(done_.cap, st_);
     /* look-back state must start as zeros (stale bits must not look like a live epoch / status) */
     ch |= tiles_.ensure(nodes_.cap / EXP_PARENTS + 2, st_, false, true);
     ch |= rs_state_.ensure((done_.cap / RS_CHUNK + 2) * 256, st_, false, true);
-    ch |= cc_state_.ensure(done_.cap / CC_CHUNK + 2, st_, false, true);
+    ch |= cc_state_.ensure(done_.cap / 256 + 2, st_, false, true); /* one word per chunk; the smallest chunk is 256 (k_compact_kept) */
     if (ch) ptrs_dirty_ = true;
   }
   void ensure_table(size_t rows) {
@@ -1851,6 +2029,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
     DevPtrs& h = *h_ptrs_;
     h.P = d_P_; h.tt = d_tt_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
+    h.surv_form = surv_form_.p; h.keep = keep_.p; h.ksend = ksend_.p; h.ksend_form = ksend_form_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
     h.form_first = form_[0].p; h.form_cnt = form_[1].p; h.form_base = form_[2].p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.events = events_.p; h.tiles = tiles_.p; h.staged = staged_.p;
@@ -1885,8 +2064,9 @@ class DeviceEngine : public Engine {
   cudaEvent_t ev_[5];
   FormDesc* h_forms_ = 0;
   DevBuf<Node> nodes_;
-  DevBuf<Row> done_, surv_, gdone_;
-  DevBuf<uint16_t> done_form_, gdone_form_;
+  DevBuf<Row> done_, surv_, gdone_, ksend_;
+  DevBuf<uint16_t> done_form_, gdone_form_, surv_form_, ksend_form_;
+  DevBuf<unsigned char> keep_;
   DevBuf<PassCtl> allctl_;
   PassCtl* h_allctl_ = 0; /* pinned, MAX_RANKS entries */
   u32 shard_min_ = 100000; /* complete expressions in the previous same-side pass from which a pass is sharded */
