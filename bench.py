@@ -318,8 +318,9 @@ def main():
             "time_to_full_report_s": tm.item() / args.steps, "expr_per_s_e2e": sexpr * args.steps / tm.item(),
             "sharded_passes": sst["sharded_passes"], "allgather_MB_per_search": sst["gather_bytes"] / 1e6,
             "stage_ms": sst["stage_ms"], "scaling": "strong",
-            "how": "forms dealt round-robin to ranks for K1; complete expressions all-gathered rank-major over NCCL; "
-                   "sort/dedupe/match/merge replicated; every rank prints the identical report",
+            "how": "forms dealt round-robin to ranks for K1; each rank sorts and pre-dedupes its own expressions "
+                   "against its table replica; the kept rows are all-gathered rank-major over NCCL; the final "
+                   "sort/dedupe/match/merge run replicated; every rank prints the identical report",
         }
 
     # whole-job numbers: sum of units over ranks, max of time over ranks
