@@ -316,7 +316,7 @@ def main():
         sharded_extra = {
             "workload": "ries %s -l%s -F3, ONE search over %d GPUs" % (args.target, args.level, world),
             "time_to_full_report_s": tm.item() / args.steps, "expr_per_s_e2e": sexpr * args.steps / tm.item(),
-            "sharded_passes": sst["sharded_passes"], "allgather_MB_per_search": sst["gather_bytes"] / 1e6,
+            "sharded_passes": sst["sharded_passes"], "allgather_MB_per_search": sst["gather_bytes"] / 1e6, "allgather_ms": sst["gather_ms"],
             "stage_ms": sst["stage_ms"], "scaling": "strong",
             "how": "forms dealt round-robin to ranks for K1; each rank sorts and pre-dedupes its own expressions "
                    "against its table replica; the kept rows are all-gathered rank-major over NCCL; the final "

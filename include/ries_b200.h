@@ -52,6 +52,7 @@ typedef struct ries_run_stats {
   unsigned long long op_count_rhs[48], op_count_lhs[48];
   /* one search over several GPUs (ries_dist_init): passes whose K1 ran sharded, bytes all-gathered */
   unsigned long long sharded_passes, gather_bytes;
+  double gather_ms;                         /* device time of those all-gathers */
 } ries_run_stats;
 void ries_last_stats(ries_run_stats *out);
 

@@ -29,6 +29,7 @@ class _Stats(ctypes.Structure):
         ("op_char", ctypes.c_char * 48), ("op_count_rhs", ctypes.c_ulonglong * 48),
         ("op_count_lhs", ctypes.c_ulonglong * 48),
         ("sharded_passes", ctypes.c_ulonglong), ("gather_bytes", ctypes.c_ulonglong),
+        ("gather_ms", ctypes.c_double),
     ]
 
 

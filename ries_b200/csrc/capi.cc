@@ -53,6 +53,7 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
     g_last.expand_nodes = r.expand_nodes;
     g_last.sharded_passes = r.sharded_passes;
     g_last.gather_bytes = r.gather_bytes;
+    g_last.gather_ms = r.gather_ms;
     for (int i = 0; i < 48; i++) {
       g_last.op_char[i] = (char)r.op_char[i];
       g_last.op_count_rhs[i] = r.op_count[0][i];

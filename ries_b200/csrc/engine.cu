@@ -1569,6 +1569,7 @@ class DeviceEngine : public Engine {
     if (const char* e = getenv("RIES_SHARD_MIN")) shard_min_ = (u32)atol(e);
     memset(h_ptrs_, 0, sizeof(DevPtrs));
     for (int i = 0; i < 5; i++) CUDA_CHECK(cudaEventCreate(&ev_[i]));
+    for (int i = 0; i < 2; i++) CUDA_CHECK(cudaEventCreate(&ev_g_[i]));
     const char* arena_env = getenv("RIES_ARENA_CAP"); /* test hook: start tiny to exercise overflow-and-rerun */
     const size_t arena0 = arena_env ? (size_t)atoi(arena_env) : (size_t)(1u << 20);
     const char* cap_env = getenv("RIES_EVENTS_CAP"); /* test hook: start tiny to exercise the regrow path */
@@ -1595,6 +1596,7 @@ class DeviceEngine : public Engine {
     cudaFreeHost(h_out_); cudaFreeHost(h_passin_); cudaFreeHost(h_ptrs_);
     if (h_events_) cudaFreeHost(h_events_);
     for (int i = 0; i < 5; i++) cudaEventDestroy(ev_[i]);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev_g_[i]);
     cudaStreamDestroy(st_);
   }
   const char* name() const override { return "sm_100a"; }
@@ -1623,6 +1625,7 @@ class DeviceEngine : public Engine {
     for (int i = 0; i < 4; i++) { stage_ms[i] = 0; stage_launches[i] = 0; }
     sort_keys = merge_rows = expand_nodes = 0;
     sharded_passes = gather_bytes = 0;
+    gather_ms = 0;
   }
 
   long inserted_before(uint32_t seq, bool inclusive) override {
@@ -1710,6 +1713,12 @@ class DeviceEngine : public Engine {
         CUDA_CHECK(cudaGetLastError());
         d2h_bytes += sizeof(PassOut);
         collect_stage_times(1, 3);
+        if (gather_pending_) {
+          float ms = 0;
+          if (cudaEventElapsedTime(&ms, ev_g_[0], ev_g_[1]) == cudaSuccess) gather_ms += ms;
+          (void)cudaGetLastError();
+          gather_pending_ = false;
+        }
       }
       const u32 ovf = h_ctl_->overflow;
       if (!ovf) break;
@@ -1776,6 +1785,7 @@ class DeviceEngine : public Engine {
   unsigned long long expand_nodes = 0;   /* live prefixes expanded (= exec'd prefixes) */
   unsigned long long sharded_passes = 0; /* passes whose K1 ran sharded over the ranks */
   unsigned long long gather_bytes = 0;   /* bytes this rank received/kept in the all-gathers */
+  double gather_ms = 0;                  /* device time of the all-gathers (CUDA events) */
   u32 table_rows() const { return nt_; }
   unsigned char sym_chars_[RIES_MAX_SYMS];
   void read_opcounts(unsigned long long* out /* [2][RIES_MAX_SYMS] */) {
@@ -1977,10 +1987,13 @@ class DeviceEngine : public Engine {
       std::vector<size_t> bytes((size_t)world), offs((size_t)world);
       size_t off = 0;
       for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].n_kept * sizeof(Row); offs[r] = off * sizeof(Row); off += all[r].n_kept; }
+      CUDA_CHECK(cudaEventRecord(ev_g_[0], st_));
       dist_allgatherv(ksend_.p, gdone_.p, bytes.data(), offs.data(), st_);
       off = 0;
       for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].n_kept * sizeof(uint16_t); offs[r] = off * sizeof(uint16_t); off += all[r].n_kept; }
       dist_allgatherv(ksend_form_.p, gdone_form_.p, bytes.data(), offs.data(), st_);
+      CUDA_CHECK(cudaEventRecord(ev_g_[1], st_));
+      gather_pending_ = true;
       gather_bytes += total * (sizeof(Row) + sizeof(uint16_t));
     }
     /* totals into the device control block, as if one K1 had produced exactly the kept expressions; from
@@ -2062,6 +2075,8 @@ class DeviceEngine : public Engine {
   SortCtl* d_sortctl_ = 0;
   u64* d_opcnt_ = 0;
   cudaEvent_t ev_[5];
+  cudaEvent_t ev_g_[2];
+  bool gather_pending_ = false;
   FormDesc* h_forms_ = 0;
   DevBuf<Node> nodes_;
   DevBuf<Row> done_, surv_, gdone_, ksend_;
@@ -2102,6 +2117,7 @@ void device_engine_report(Engine* e, DeviceReport* r) {
   r->expand_nodes = d->expand_nodes;
   r->sharded_passes = d->sharded_passes;
   r->gather_bytes = d->gather_bytes;
+  r->gather_ms = d->gather_ms;
   r->table_rows = d->table_rows();
   d->read_opcounts(&r->op_count[0][0]);
   memcpy(r->op_char, d->sym_chars_, sizeof(r->op_char));

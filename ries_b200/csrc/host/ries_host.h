@@ -140,6 +140,7 @@ struct DeviceReport {
   unsigned long long stage_launches[4];
   unsigned long long sort_keys, merge_rows, expand_nodes, table_rows;
   unsigned long long sharded_passes, gather_bytes;
+  double gather_ms;
   unsigned long long op_count[2][RIES_MAX_SYMS]; /* exec() calls per symbol: [0] RHS passes, [1] LHS passes */
   unsigned char op_char[RIES_MAX_SYMS];
 };

@@ -50,7 +50,7 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = ok and bool(flag.item())
         report.append({"case": name, "identical_on_every_rank": bool(flag.item()), "seconds": round(dt, 4),
-                       "sharded_passes": st["sharded_passes"], "gather_MB": round(st["gather_bytes"] / 1e6, 1),
+                       "sharded_passes": st["sharded_passes"], "gather_MB": round(st["gather_bytes"] / 1e6, 1), "gather_ms": round(st["gather_ms"], 2),
                        "stage_ms": [round(x, 2) for x in st["stage_ms"]]})
     ries_b200.dist_finalize()
     if rank == 0:
