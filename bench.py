@@ -354,7 +354,7 @@ def main():
     stages = [
         ("K1 enumerate+evaluate (k_expand)", k1_bytes, dev_ms[0], dev_launches[0]),
         ("K2 order+radix sort (k_reorder/k_rs_onesweep)", sort_bytes, dev_ms[1], dev_launches[1]),
-        ("K2/K3 classify+match+merge (k_classify/k_match/k_merge_*)", merge_bytes, dev_ms[2], dev_launches[2]),
+        ("K2/K3 classify+match+merge (k_classify_compact/k_match_merge_new/k_merge_old)", merge_bytes, dev_ms[2], dev_launches[2]),
     ]
     dom = max(stages, key=lambda s: s[2])
     achieved = dom[1] / (dom[2] / 1e3) / 1e9 if dom[2] > 0 else 0.0
