@@ -133,3 +133,18 @@ def test_gpu_batch_of_targets_matches_reference(product_lib, oracle_build):
     # and the same batch again gives the same bytes (engines are reused, streams interleave differently)
     again = ries_b200.batch(targets, flags, workers=5)
     assert [normalise(a[1]) for a in again] == [normalise(g[1]) for g in got]
+
+
+def test_gpu_one_search_over_two_gpus(product_lib):
+    """North-star row (e): two ranks join an NCCL communicator through the C ABI and run ONE search together
+    (K1 sharded by forms, local pre-dedupe, rank-major all-gather); both must print the golden bytes."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the virtual-rank variant of the same path runs in test_gpu_pass_variants_agree)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "l5", "t25063_l3_F3_x"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
