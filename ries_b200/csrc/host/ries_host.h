@@ -61,6 +61,12 @@ struct Options {
   bool allow_slow_message = true;
   bool no_cv_simplify = false;
   bool solve_for_x = false; /* -s / --try-solve-for-x (ries.c:11756) */
+  double derivative_margin = 0;       /* --derivative-margin (11284): 0 = automatic */
+  double min_equ_val = -9.9e99, max_equ_val = 9.9e99; /* --min/--max-equate-value (11484, 11373) */
+  double sincos_max_arg = 1.0;        /* --max-trig-cycles (11536) */
+  double sig_loss = 0.01;             /* --significance-loss-margin (11622) */
+  bool match_all_digits = false;      /* --match-all-digits / --mad (11366) */
+  bool explicit_multiply = false;     /* --explicit-multiply (11338) */
   bool refinement = true;   /* --no-refinement (11577): the threshold never shrinks; every match inside it is printed once */
   bool one_sided = false;   /* --one-sided (11600): 'x' is the only LHS, RHS passes from then on (12425) */
   bool anagram = false;     /* --numeric-anagram (11586): digit budget through sa_alwd, implies one_sided */

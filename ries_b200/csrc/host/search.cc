@@ -854,6 +854,7 @@ struct Search {
     }
     finish_setup(opt, S, out);
     icx.S = &S;
+    icx.explicit_multiply = opt.explicit_multiply;
     best_match = S.init_match_dist;
     nr_init();
 

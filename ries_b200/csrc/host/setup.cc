@@ -163,6 +163,7 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       double t;
       if (v && sscanf(v, "%lf", &t) > 0) {
         o.k_max_match_dist = t;
+        o.match_all_digits = false; /* cannot use both options together (11400) */
         if (t < 0) out.printf("First match must be closer than %g times your target value.\n", -t);
         else if (t == 0) out.printf("Only give an 'exact' match (if any) then exit.\n");
         else out.printf("First match must be closer than %g.\n", t);
@@ -192,6 +193,128 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       }
     } else if (strcmp(a, "--no-slow-messages") == 0) {
       o.allow_slow_message = false;
+    } else if (strcmp(a, "--derivative-margin") == 0) { /* ries.c:11284 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        if (t < 0) {
+          out.printf("%s: --derivative-margin must be positive (I got %g).\n\n", o.argv0.c_str(), t);
+          brief_help(out);
+          throw ExitRequest{-1};
+        } else if (t > 1.0e-4) {
+          out.printf("%s: --derivative-margin value should be at most 1.0e-4.\n\n", o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        } else {
+          o.derivative_margin = t;
+          out.printf("Allowing d/dx to be as small as value times %g.\n", t);
+        }
+      } else {
+        out.printf("%s: --derivative-margin should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--explicit-multiply") == 0) { /* 11338 */
+      o.explicit_multiply = true;
+    } else if ((strcmp(a, "--match-all-digits") == 0) || (strcmp(a, "--mad") == 0)) { /* 11366 */
+      o.match_all_digits = true;
+      o.k_max_match_dist = -0.01;
+    } else if (strcmp(a, "--max-equate-value") == 0) { /* 11373 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        if (t <= o.min_equ_val) {
+          out.printf("%s: --max-equate-value argument cannot be greater than --min-equate-value argument.\n",
+                     o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        }
+        o.max_equ_val = t;
+        out.printf("Equations will have both sides at most %s\n", spfg(15, t).c_str());
+      } else {
+        out.printf("%s: --max-equate-value should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--min-equate-value") == 0) { /* 11484 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        if (t >= o.max_equ_val) {
+          out.printf("%s: --min-equate-value argument cannot be greater than --max-equate-value argument.\n",
+                     o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        }
+        o.min_equ_val = t;
+        out.printf("Equations will have both sides at least %s\n", spfg(15, t).c_str());
+      } else {
+        out.printf("%s: --min-equate-value should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--min-match-distance") == 0) { /* 11506 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        o.min_matchsize = t;
+        if (t == 0.0) {
+          out.printf("Will exit if an 'exact' match is found.\n");
+          o.exact_exit = true;
+        } else if (t < -0.1) {
+          out.printf("%s: --min-match-distance argument can be negative but not less than -0.1\n\n",
+                     o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        } else if (t < 0.0) {
+          out.printf("Using a minimum match distance of %g times your target value.\n", t);
+        } else {
+          out.printf("Using minimum match distance: %g\n", t);
+        }
+      } else {
+        out.printf("%s: --min-match-distance should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--max-trig-cycles") == 0) { /* 11536 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        if ((t > 0.0) && (t <= 100.0)) {
+          o.sincos_max_arg = t;
+          out.printf("Arguments of trig functions will be restricted to %s cycles on either side of zero.\n",
+                     spfg(15, t * 0.5).c_str());
+        } else {
+          out.printf("%s: --max-trig-cycles must be between 0.0 and 100.0\n\n", o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        }
+      } else {
+        out.printf("%s: --max-trig-cycles should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--relative-roots") == 0) { /* 11609 */
+      if (o.match_all_digits) out.printf("Note: Ignoring '%s' because '--match-all-digits' is set.\n", a);
+      else o.relative_x = true;
+    } else if (strcmp(a, "--significance-loss-margin") == 0) { /* 11622 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        if ((t >= 0.0) && (t < 100.0)) {
+          o.sig_loss = pow(10.0, -t);
+          out.printf("Using significance loss margin: %g\n", o.sig_loss);
+        } else {
+          out.printf("%s: --significance-loss-margin must be between 0.0 and 100.0\n\n", o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        }
+      } else {
+        out.printf("%s: --significance-loss-margin should be followed by a numeric argument.\n\n",
+                   o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
     } else if (strcmp(a, "--no-refinement") == 0) { /* ries.c:11577 */
       o.refinement = false;
     } else if (strcmp(a, "--one-sided") == 0) { /* ries.c:11600 */
@@ -501,13 +624,13 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
   }
   P.sincos_scale = P.k_pi; /* default trig scale (10158) */
   P.trig_scale_default = 1;
-  P.trig_max_arg = P.k_pi * 1.0; /* k_pi * k_sincos_max_arg */
+  P.trig_max_arg = P.k_pi * o.sincos_max_arg; /* k_pi * k_sincos_max_arg (5503) */
   P.k_sin_clip = 0.99999;
   P.k_eXlim = 690.0;
-  P.k_sig_loss = 0.01;
+  P.k_sig_loss = o.sig_loss;
   P.k_newton_settled = 1.0e-15;
-  P.min_equ_val = -9.9e99;
-  P.max_equ_val = 9.9e99;
+  P.min_equ_val = o.min_equ_val;
+  P.max_equ_val = o.max_equ_val;
   P.tg_phi = TYPE_CONS;
   P.tg_e = TYPE_TCEL;
   P.tg_pi = TYPE_TCEL;
@@ -653,11 +776,25 @@ void finish_setup(Options& o, Setup& S, const Sink& out) {
   P.restrict_trig_args = o.restrict_trig_args;
 
   S.tgt_to_print = o.target;
+  if (o.match_all_digits) { /* 12199-12229 */
+    if (o.mag_ulp > 0) {
+      o.k_max_match_dist = o.mag_ulp * 0.5;
+      if (o.target < 0) o.target -= o.k_max_match_dist;
+      else o.target += o.k_max_match_dist;
+      if (P.targ_tags == TYPE_INT) P.targ_tags = TYPE_RAT;
+      if (!o.wide_output) o.relative_x = false;
+    } else {
+      out.printf("Ignoring --match-all-digits option because I could not determine\n"
+                 "the magnitude of the ULP (unit in the last place).\n");
+    }
+  }
   P.target = o.target;
 
-  /* k_vanished_dx auto-scaling (12231-12240) */
+  /* k_vanished_dx: given, or auto-scaled (12231-12240) */
   P.k_vanished_dx = 1.0e-6;
-  if (fabs(o.target) * P.k_vanished_dx > 0.1) {
+  if (o.derivative_margin > 0) {
+    P.k_vanished_dx = o.derivative_margin;
+  } else if (fabs(o.target) * P.k_vanished_dx > 0.1) {
     P.k_vanished_dx = 0.1 / fabs(o.target);
     out.printf("Auto-setting --derivative-margin %g\n", P.k_vanished_dx);
   } else if (fabs(o.target) < 1.0e-8) {
@@ -676,7 +813,12 @@ void finish_setup(Options& o, Setup& S, const Sink& out) {
     throw ExitRequest{-1};
   }
   if (fabs(o.target) / P.k_vanished_dx >= 1.0e15) { /* 12264 */
-    if (o.sa_alwd[(unsigned char)'x'] > 1) {
+    if (o.sa_alwd[(unsigned char)'x'] > 1 && o.derivative_margin > 0) {
+      out.printf("WARNING: Your --derivative-margin option (%g)\n"
+                 "  is so small that RIES might report tautologies like x/x = 1. To avoid\n"
+                 "  this warning, use the option -Ox or give a target value smaller than\n"
+                 "  %g.\n\n", o.derivative_margin, 10.0 / 1.0e-6);
+    } else if (o.sa_alwd[(unsigned char)'x'] > 1) {
       out.printf("WARNING: Your target value is so large that RIES might report tautologies\n"
                  "  like x/(x/3) = 3. To avoid this warning, use the option -Ox or give a\n"
                  "  target value smaller than %g.\n\n", 10.0 / 1.0e-6);

@@ -10,7 +10,7 @@ from conftest import ROOT, golden_cases, golden_text, run_binary
 SMALL = [c for c in golden_cases(big=False) if c["name"] not in ("t25063_l4_F3", "infix_l4")]
 # the C restatement covers the postfix/FORTH formats (-F0/-F3); infix is checked through the emulation + GPU
 # ... and not --no-refinement (host-only bookkeeping shared by the emulation and the product)
-POSTFIX = [c for c in SMALL if not c["name"].startswith(("infix_", "cfg1_", "solve_", "web_", "norefine_"))
+POSTFIX = [c for c in SMALL if not c["name"].startswith(("infix_", "cfg1_", "solve_", "web_", "norefine_", "opt_"))
            and "infix" not in c["name"]]
 
 
