@@ -1496,6 +1496,11 @@ struct DevBuf {
     if (n <= cap) return false;
     size_t ncap = std::max(n, cap + cap / 2);
     T* q = 0;
+    if (!(keep && p && cap) && p) { /* nothing to carry over: give the old block back first, so the pool can
+                                       reuse its physical memory for the bigger one */
+      CUDA_CHECK(cudaFreeAsync(p, st));
+      p = 0;
+    }
     CUDA_CHECK(cudaMallocAsync(&q, ncap * sizeof(T), st));
     if (zero) CUDA_CHECK(cudaMemsetAsync(q, 0, ncap * sizeof(T), st));
     if (keep && p && cap) CUDA_CHECK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
