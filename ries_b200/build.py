@@ -30,7 +30,7 @@ def sources():
     out = []
     for root, _, files in os.walk(CSRC):
         for f in files:
-            if f.endswith((".cu", ".cc", ".h", ".c")):
+            if f.endswith((".cu", ".cuh", ".cc", ".h", ".c", ".inc")):
                 out.append(os.path.join(root, f))
     out.append(os.path.join(HERE, "..", "include", "ries_b200.h"))
     return out

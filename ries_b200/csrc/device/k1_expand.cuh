@@ -1,0 +1,330 @@
+// K1: enumerate + evaluate one expression position of every live prefix (ge_2 + exec).
+// Part of the single translation unit engine.cu (included inside namespace ries).
+#pragma once
+
+/* ---------------------------------------------------------------- K1: enumerate+evaluate - */
+
+/* K1 works on tiles of 256 consecutive live prefixes (one block per tile at a time):
+     phase 1  thread = prefix: the integer symbol-append tests for all candidate symbols -> bit mask
+     phase 2  the (prefix, symbol) pairs that passed are listed in shared memory GROUPED BY SYMBOL SLOT
+     phase 3  thread = listed pair: exec + value prunes; warps are (almost) operator-uniform
+     phase 4  ordered append: children land in (prefix, symbol) order = the reference's DFS order
+   The last block to leave advances the frontier for the next level. */
+#ifndef EXP_THREADS
+#define EXP_THREADS 256
+#endif
+#define EXP_PARENTS EXP_THREADS
+#define EXP_MAX_ITEMS (EXP_PARENTS * RIES_SLOTS)
+#ifndef EXP_MIN_BLOCKS
+#define EXP_MIN_BLOCKS 3
+#endif
+#define IT_LIVE 0x4000u
+#define IT_DONE 0x8000u
+
+#define TS_AGG (1ull << 62)
+#define TS_INC (2ull << 62)
+#define TS_STATUS(x) ((x) >> 62)
+#define TS_LIVE(x) ((u32)(((x) >> 31) & 0x7fffffffull))
+#define TS_DONE(x) ((u32)((x)&0x7fffffffull))
+#define TS_PACK(st, live, done) ((st) | ((u64)(live) << 31) | (u64)(done))
+
+/* Decoupled look-back over tile aggregates (two counters packed in one word), in two steps so that a
+   block can publish a tile's aggregate, go on to the next tile, and only then resolve the first one's
+   exclusive prefix (by then its predecessors have long published). */
+__device__ __forceinline__ void tile_publish(volatile u64* state, u32 tile, u32 live_agg, u32 done_agg) {
+  __threadfence();
+  state[tile] = TS_PACK(tile == 0 ? TS_INC : TS_AGG, live_agg, done_agg);
+}
+
+/* Called by warp 0. */
+__device__ __forceinline__ void tile_lookback(volatile u64* state, u32 tile, u32 live_agg, u32 done_agg,
+                                              u32& live_excl, u32& done_excl) {
+  const u32 lane = threadIdx.x & 31;
+  live_excl = 0; done_excl = 0;
+  if (tile == 0) return;
+  u32 lsum = 0, dsum = 0;
+  int idx = (int)tile - 1;
+  while (true) {
+    int my = idx - (int)lane;
+    u64 w;
+    if (my >= 0) {
+      do { w = state[my]; } while (TS_STATUS(w) == 0);
+    } else {
+      w = TS_PACK(TS_INC, 0, 0);
+    }
+    u32 inc_mask = __ballot_sync(0xffffffffu, TS_STATUS(w) == 2);
+    /* lanes closer than the first inclusive one contribute their aggregates; that one its prefix */
+    u32 first_inc = inc_mask ? (u32)__ffs(inc_mask) - 1 : 32;
+    u32 lv = (lane <= first_inc) ? TS_LIVE(w) : 0;
+    u32 dv = (lane <= first_inc) ? TS_DONE(w) : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      lv += __shfl_xor_sync(0xffffffffu, lv, o);
+      dv += __shfl_xor_sync(0xffffffffu, dv, o);
+    }
+    lsum += lv; dsum += dv;
+    if (inc_mask) break;
+    idx -= 32;
+  }
+  if (lane == 0) {
+    __threadfence();
+    state[tile] = TS_PACK(TS_INC, lsum + live_agg, dsum + done_agg);
+  }
+  live_excl = lsum; done_excl = dsum;
+}
+
+/* Shared-memory state of one tile between its front half (phases 1-3) and its back half (phase 4). */
+struct TileBuf {
+  Node par[EXP_PARENTS];
+  unsigned short item[EXP_MAX_ITEMS];
+  u32 live[EXP_PARENTS], done[EXP_PARENTS];   /* per prefix: bit per slot */
+  u32 lbase[EXP_PARENTS], dbase[EXP_PARENTS]; /* per prefix: exclusive child offsets inside the tile */
+  unsigned char cls[EXP_PARENTS], complete[EXP_PARENTS];
+  u32 total, tile, live_agg, done_agg;
+};
+
+#define EXP_DYN_SMEM (2 * sizeof(TileBuf))
+
+__global__ void __launch_bounds__(EXP_THREADS, EXP_MIN_BLOCKS)
+k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  TileBuf* s_buf = (TileBuf*)s_dyn; /* [2] */
+  __shared__ u32 s_opcnt[RIES_MAX_SYMS];
+  __shared__ RiesParams P;
+  __shared__ TestTables TT;
+  __shared__ u32 s_wcnt[EXP_THREADS / 32][RIES_SLOTS];
+  __shared__ u32 s_slot_base[RIES_SLOTS];
+  __shared__ u32 s_wl[EXP_THREADS / 32], s_wd[EXP_THREADS / 32];
+  __shared__ u32 s_live_base, s_done_base, s_dead, s_tile, s_last, s_next;
+
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lvl_begin = ctl->lvl_begin, lvl_end = ctl->lvl_end;
+  const u32 n = lvl_end - lvl_begin;
+  const u32 ntiles = (n + EXP_PARENTS - 1) / EXP_PARENTS;
+  const DevPtrs D = *Dp;
+  const int using_x = Ap->using_x, cplx = Ap->cplx;
+  const u32 cap_nodes = Ap->cap_nodes, cap_done = Ap->cap_done;
+  if (ntiles != 0 && !(ctl->overflow & (OVF_NODES | OVF_DONE))) {
+    {
+      const u32* src = (const u32*)D.P;
+      u32* dst = (u32*)&P;
+      for (u32 i = tid; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];
+      const u32* tsrc = (const u32*)D.tt;
+      u32* tdst = (u32*)&TT;
+      for (u32 i = tid; i < sizeof(TestTables) / 4; i += EXP_THREADS) tdst[i] = tsrc[i];
+      if (tid == 0) s_dead = 0;
+      if (tid < RIES_MAX_SYMS) s_opcnt[tid] = 0;
+    }
+    __syncthreads();
+    const u32 done_base0 = ctl->done_count; /* read-only during the tile loop (updated by the last block) */
+    const u32 lt = (1u << lane) - 1;
+    Node* nodes = D.nodes;
+    const FormDesc* forms = D.forms;
+    volatile u64* tile_state = (volatile u64*)D.tiles;
+    u32 my_dead = 0;
+    int cur = 0;
+    bool have_prev = false;
+
+    /* Tiles are handed out by ticket, so a tile's predecessors (which its look-back waits on) are always
+       held by blocks that are already running: safe even when not every block of the grid is resident
+       (several engines sharing the GPU on different streams).  The loop is software-pipelined: the front
+       half of tile t+1 runs between the publication of tile t's aggregate and t's look-back. */
+    while (true) {
+      if (tid == 0) { s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next = 0; }
+      __syncthreads();
+      const u32 tile = s_tile;
+      const bool have_cur = tile < ntiles;
+      if (have_cur) {
+        TileBuf& B = s_buf[cur];
+        Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + cur) * EXP_MAX_ITEMS;
+        const u32 p0 = lvl_begin + tile * EXP_PARENTS;
+        /* ---- phase 1: integer tests, one thread per prefix ---- */
+        u32 mask = 0;
+        {
+          const u32 p = p0 + tid;
+          if (p < lvl_end) {
+            const Node par = nodes[p];
+            B.par[tid] = par;
+            const FormDesc& F = forms[par.form];
+            const int cls = F.cls[par.len];
+            const int ns = P.cls_n[cls];
+            const int atts = prefix_attrs(P, F, par, using_x);
+            mask = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
+            my_dead += (u32)ns - (u32)__popc(mask);
+            B.cls[tid] = (unsigned char)cls;
+            B.complete[tid] = (unsigned char)(par.len + 1 >= F.flen);
+          }
+          B.live[tid] = 0;
+          B.done[tid] = 0;
+        }
+        /* ---- phase 2: list the surviving pairs grouped by slot ---- */
+#pragma unroll
+        for (int k = 0; k < RIES_SLOTS; k++) {
+          u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
+          if (lane == 0) s_wcnt[warp][k] = __popc(b);
+        }
+        __syncthreads();
+        if (tid < RIES_SLOTS) { /* per slot: exclusive prefix over warps, and the slot's total */
+          u32 run = 0;
+          for (int w = 0; w < EXP_THREADS / 32; w++) { u32 c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+          s_slot_base[tid] = run;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          u32 run = 0;
+          for (int k = 0; k < RIES_SLOTS; k++) { u32 c = s_slot_base[k]; s_slot_base[k] = run; run += c; }
+          B.total = run;
+          B.tile = tile;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RIES_SLOTS; k++) {
+          u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
+          if ((mask >> k) & 1u) B.item[s_slot_base[k] + s_wcnt[warp][k] + __popc(b & lt)] = (unsigned short)((tid << 4) | k);
+        }
+        __syncthreads();
+        const u32 T = B.total;
+        /* ---- phase 3: exec + value prunes; warps pull 32 listed pairs at a time (a warp's batch is
+           almost always one operator, and heavy operators spread over the warps) ---- */
+        while (true) {
+          u32 b0 = 0;
+          if (lane == 0) b0 = atomicAdd(&s_next, 32u);
+          b0 = __shfl_sync(0xffffffffu, b0, 0);
+          if (b0 >= T) break;
+          const u32 i = b0 + lane;
+          if (i < T) {
+            const u32 it = B.item[i];
+            const u32 pl = it >> 4, k = it & 15u;
+            const int cls = B.cls[pl];
+            const int g = P.trial[cls][k];
+            Node child;
+            atomicAdd(&s_opcnt[g], 1u); /* exec() calls per symbol: the algorithmic work of this kernel */
+            int oc = expand_exec(P, cls, g, B.complete[pl] != 0, nodes, B.par[pl], p0 + pl, using_x, child);
+            if (oc == OUT_DEAD) my_dead++;
+            else if (oc == OUT_LIVE || oc == OUT_DONE) {
+              Staged st;
+              st.val = child.val; st.der = child.der; st.below = child.below; st.tag = child.tag; st.sp = child.sp;
+              st.pad0 = 0; st.pad1 = 0;
+              staged[i] = st;
+              if (oc == OUT_LIVE) { atomicOr(&B.live[pl], 1u << k); B.item[i] = (unsigned short)(it | IT_LIVE); }
+              else { atomicOr(&B.done[pl], 1u << k); B.item[i] = (unsigned short)(it | IT_DONE); }
+            }
+          }
+        }
+        __syncthreads();
+        /* child offsets inside the tile, and the tile's aggregate -> published at once */
+        {
+          u32 nl = __popc(B.live[tid]), nd = __popc(B.done[tid]);
+          u32 il = nl, id = nd;
+          for (int o = 1; o < 32; o <<= 1) {
+            u32 a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, id, o);
+            if (lane >= (u32)o) { il += a; id += b; }
+          }
+          if (lane == 31) { s_wl[warp] = il; s_wd[warp] = id; }
+          __syncthreads();
+          u32 wl = 0, wd = 0, la = 0, da = 0;
+          for (u32 w = 0; w < EXP_THREADS / 32; w++) {
+            const u32 a = s_wl[w], b = s_wd[w];
+            if (w < warp) { wl += a; wd += b; }
+            la += a; da += b;
+          }
+          B.lbase[tid] = wl + il - nl;
+          B.dbase[tid] = wd + id - nd;
+          if (tid == 0) {
+            B.live_agg = la; B.done_agg = da;
+            tile_publish(tile_state, tile, la, da);
+          }
+        }
+      }
+      /* ---- phase 4 of the PREVIOUS tile: ordered append ---- */
+      if (have_prev) {
+        TileBuf& B = s_buf[cur ^ 1];
+        const Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * EXP_MAX_ITEMS;
+        if (warp == 0) {
+          u32 le, de;
+          tile_lookback(tile_state, B.tile, B.live_agg, B.done_agg, le, de);
+          if (lane == 0) { s_live_base = le; s_done_base = de; }
+        }
+        __syncthreads();
+        const u32 T = B.total;
+        const u32 p_tile = B.tile;
+        (void)p_tile;
+        for (u32 i = tid; i < T; i += EXP_THREADS) {
+          const u32 it = B.item[i];
+          if (!(it & (IT_LIVE | IT_DONE))) continue;
+          const u32 pl = (it >> 4) & 1023u, k = it & 15u;
+          const Node& par = B.par[pl];
+          const int g = P.trial[B.cls[pl]][k];
+          const Staged st = staged[i];
+          Node child;
+          child.val = st.val; child.der = st.der; child.below = st.below; child.tag = st.tag; child.sp = st.sp;
+          expand_finish(P, par, g, child);
+          const u32 below_k = (1u << k) - 1;
+          if (it & IT_LIVE) {
+            u32 pos = lvl_end + s_live_base + B.lbase[pl] + __popc(B.live[pl] & below_k);
+            if (pos < cap_nodes) nodes[pos] = child;
+          } else {
+            u32 pos = done_base0 + s_done_base + B.dbase[pl] + __popc(B.done[pl] & below_k);
+            if (pos < cap_done) {
+              Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
+              D.done[pos] = r;
+              D.done_form[pos] = child.form;
+            }
+          }
+        }
+      }
+      __syncthreads(); /* s_tile, s_live_base and the buffers are reused by the next round */
+      if (!have_cur) break;
+      have_prev = true;
+      cur ^= 1;
+    }
+    /* block-level dead-end count -> one atomic per block */
+    for (int o = 16; o > 0; o >>= 1) my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
+    if (lane == 0 && my_dead) atomicAdd(&s_dead, my_dead);
+    __syncthreads();
+    if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
+    if (tid < RIES_MAX_SYMS && s_opcnt[tid]) atomicAdd(&D.opcnt[(using_x ? RIES_MAX_SYMS : 0) + tid], (u64)s_opcnt[tid]);
+  }
+
+  /* ---- level finish by the last block to get here (replaces a separate launch) ---- */
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile u64* tile_state = (volatile u64*)D.tiles;
+  const u64 last = ntiles ? tile_state[ntiles - 1] : 0;
+  __syncthreads();
+  for (u32 i = tid; i < ntiles; i += EXP_THREADS) tile_state[i] = 0;
+  if (tid == 0) {
+    u32 ovf = ctl->overflow;
+    if (!(ovf & (OVF_NODES | OVF_DONE))) {
+      u32 live = TS_LIVE(last), dn = TS_DONE(last);
+      u64 new_nodes = (u64)lvl_end + live;
+      u64 new_done = (u64)ctl->done_count + dn;
+      if (new_nodes > cap_nodes) ovf |= OVF_NODES;
+      if (new_done > cap_done) ovf |= OVF_DONE;
+      ctl->overflow = ovf;
+      ctl->lvl_begin = lvl_end;
+      /* on overflow stop expanding: the host grows the arenas and reruns the pass */
+      ctl->lvl_end = (ovf & (OVF_NODES | OVF_DONE)) ? lvl_end : (u32)new_nodes;
+      ctl->node_count = (new_nodes > 0xffffffffull) ? 0xffffffffu : (u32)new_nodes;
+      ctl->done_count = (new_done > 0xffffffffull) ? 0xffffffffu : (u32)new_done;
+    }
+    ctl->tile_ticket = 0;
+    ctl->blocks_done = 0;
+  }
+}
+
+/* fp64 FMA peak of this device, measured (denominator for K1's fp64 figure): 8 independent chains/thread */
+__global__ void k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

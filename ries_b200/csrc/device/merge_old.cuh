@@ -1,0 +1,81 @@
+// Merge of the old table rows (window of the gap list in shared memory).
+// Part of the single translation unit engine.cu (included inside namespace ries).
+#pragma once
+
+/* Upper bound by a whole warp over a sorted u32 array: #{u : a[u] <= key}. */
+__device__ __forceinline__ u32 warp_upper_bound_u32(const u32* __restrict__ a, u32 n, u32 key) {
+  const u32 lane = threadIdx.x & 31;
+  u32 lo = 0, hi = n;
+  while (hi - lo > 32) {
+    const u32 step = (hi - lo + 32) / 33;
+    const u32 q = lo + (lane + 1) * step - 1;
+    const bool le = (q < hi) && (a[q] <= key);
+    const u32 c = __popc(__ballot_sync(0xffffffffu, le));
+    const u32 nhi = lo + (c + 1) * step - 1;
+    lo += c * step;
+    if (c < 32 && nhi < hi) hi = nhi;
+  }
+  const bool le = (lo + lane < hi) && (a[lo + lane] <= key);
+  return lo + __popc(__ballot_sync(0xffffffffu, le));
+}
+
+/* Old rows move up by the number of new rows whose gap is at or below them.  A chunk of consecutive
+   old rows only needs the slice of the (sorted) gap list between the counts of its first and last row:
+   found by two warp searches, staged in shared memory, searched there. */
+#define MO_THREADS 256
+#define MO_ITEMS 8
+#define MO_CHUNK (MO_THREADS * MO_ITEMS)
+#define MO_WIN 4096
+__global__ void __launch_bounds__(MO_THREADS)
+k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
+  __shared__ u32 s_win[MO_WIN];
+  __shared__ u32 s_lo, s_hi;
+  if (C->overflow) return;
+  const u32 nu = C->n_uniq;
+  if (nu == 0) return; /* nothing inserted: the live buffer stays as it is */
+  const u32 nt = T->nt;
+  const DevPtrs D = *Dp;
+  const Row* __restrict__ trow = D.trow[T->cur];
+  Row* mrow = D.trow[T->cur ^ 1];
+  double* mval = D.tval[T->cur ^ 1];
+  const u32* __restrict__ uniq_gap = D.uniq_gap;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  (void)lane;
+  const u32 nchunks = (nt + MO_CHUNK - 1) / MO_CHUNK;
+  for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const u32 base = chunk * MO_CHUNK;
+    const u32 last = min(base + MO_CHUNK, nt) - 1;
+    if (warp == 0) {
+      u32 r = warp_upper_bound_u32(uniq_gap, nu, base);
+      if (lane == 0) s_lo = r;
+    } else if (warp == 1) {
+      u32 r = warp_upper_bound_u32(uniq_gap, nu, last);
+      if (lane == 0) s_hi = r;
+    }
+    __syncthreads();
+    const u32 lo = s_lo, wn = s_hi - s_lo;
+    const bool in_smem = wn <= MO_WIN;
+    if (in_smem)
+      for (u32 j = tid; j < wn; j += MO_THREADS) s_win[j] = uniq_gap[lo + j];
+    __syncthreads();
+    const u32* win = in_smem ? s_win : uniq_gap + lo;
+#pragma unroll
+    for (int r = 0; r < MO_ITEMS; r++) {
+      const u32 j = base + r * MO_THREADS + tid;
+      if (j < nt) {
+        u32 a = 0, b = wn;
+        if (wn) {
+          while (a < b) {
+            u32 mid = (a + b) >> 1;
+            if (win[mid] <= j) a = mid + 1; else b = mid;
+          }
+        }
+        const Row row = trow[j];
+        const u32 dst = j + lo + a;
+        mrow[dst] = row;
+        mval[dst] = row.val;
+      }
+    }
+    __syncthreads();
+  }
+}

@@ -1,0 +1,46 @@
+// Pass begin / end kernels.
+// Part of the single translation unit engine.cu (included inside namespace ries).
+#pragma once
+
+/* ---------------------------------------------------------------- pass begin / end ------ */
+
+__global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+  const u32 nforms = (u32)A->nforms;
+  const u32 world = (u32)A->shard_world, rank = (u32)A->shard_rank;
+  const u32 nroots = (nforms > rank) ? (nforms - rank + world - 1) / world : 0; /* forms dealt round-robin */
+  for (u32 j = threadIdx.x; j < nroots; j += blockDim.x) {
+    Node r;
+    r.val = 0; r.der = 0; r.sym.lo = 0; r.sym.hi = 0;
+    r.below = RIES_NO_NODE; r.form = (uint16_t)(rank + j * world); r.cplx = 0; r.tag = 0; r.len = 0; r.sp = 0;
+    r.pad0 = 0; r.pad1 = 0;
+    D->nodes[j] = r;
+  }
+  for (u32 i = threadIdx.x; i < nforms; i += blockDim.x) {
+    D->form_first[i] = 0;
+    D->form_cnt[i] = 0;
+  }
+  u32* sc = (u32*)D->sortctl;
+  for (u32 i = threadIdx.x; i < sizeof(SortCtl) / 4; i += blockDim.x) sc[i] = 0;
+  if (threadIdx.x == 0) {
+    C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
+    C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
+    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0;
+    u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
+    if (e == 0) e = 16;
+    T->epoch = e;
+  }
+}
+
+__global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+  if (threadIdx.x == 0 && !C->overflow && C->n_uniq) {
+    T->cur ^= 1u;
+    T->nt += C->n_uniq;
+  }
+  /* the first few candidates ride along with the counters (C is the head of a PassOut) */
+  u32 ne = C->n_events;
+  if (ne > A->cap_events) ne = A->cap_events;
+  if (ne > HEAD_EVENTS) ne = HEAD_EVENTS;
+  const u32* src = (const u32*)D->events;
+  u32* dst = (u32*)((PassOut*)C)->head;
+  for (u32 i = threadIdx.x; i < ne * (sizeof(MatchEvent) / 4); i += blockDim.x) dst[i] = src[i];
+}
