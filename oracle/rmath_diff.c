@@ -49,9 +49,11 @@ int main(int argc, char **argv) {
       a = pow(x, y); b = rmh_pow(x, y);
     } else if (!strcmp(f, "sincos")) {
       x = mode == 0 ? -M_PI + 2 * M_PI * unif() : mode == 1 ? logu(-30, 2, 1) : mode == 2 ? logu(-3, 26, 1) : M_PI * (double)((long)(rnd() % 2001) - 1000) / 1000.0;
+      if (rnd() % 4 == 0) x = -400 + 800 * unif(); /* --max-trig-cycles: to 100 pi */
       sincos(x, &a, &a2); rmh_sincos(x, &b, &b2); y = 0;
     } else if (!strcmp(f, "tan")) {
       x = mode == 0 ? -M_PI + 2 * M_PI * unif() : mode == 1 ? logu(-30, 2, 1) : mode == 2 ? -25 + 50 * unif() : M_PI * (double)((long)(rnd() % 2001) - 1000) / 1000.0;
+      if (rnd() % 4 == 0) x = (rnd() % 2) ? -400 + 800 * unif() : logu(4, 26, 1); /* --max-trig-cycles: to 100 pi, and up to 1e8 */
       a = tan(x); b = rmh_tan(x); y = 0;
     } else {
       y = mode == 0 ? logu(-34, 34, 1) : mode == 1 ? -10 + 20 * unif() : mode == 2 ? logu(-3, 3, 1) : (double)((long)(rnd() % 19) - 9);

@@ -409,8 +409,9 @@ RIES_HD void rm_sincos(double x, double* sinx, double* cosx) {
 }
 
 /* ------------------------------------------------------------------------------------------
-   tan -- sysdeps/ieee754/dbl-64/s_tan.c (IBM), |x| <= 25: odd polynomial to 0.0608, the
-   186-entry {x, tan, cot} table to 0.787, reduction by pi/2 with tan / -cot above.
+   tan -- sysdeps/ieee754/dbl-64/s_tan.c (IBM), |x| <= 1e8: odd polynomial to 0.0608, the
+   186-entry {x, tan, cot} table to 0.787, reduction by pi/2 with tan / -cot above (one extra term of
+   pi/2 to 25, two extra terms beyond: --max-trig-cycles lets exec() reach 100 pi).
    ------------------------------------------------------------------------------------------ */
 RIES_HD double rm_tan_poly(double a2) { /* d3 + a2 (d5 + a2 (d7 + a2 (d9 + a2 d11))) */
   const double d3 = 0x1.5555555555555p-2, d5 = 0x1.11111111107c6p-3, d7 = 0x1.ba1ba1cdb8745p-5,
@@ -420,7 +421,7 @@ RIES_HD double rm_tan_poly(double a2) { /* d3 + a2 (d5 + a2 (d7 + a2 (d9 + a2 d1
 
 RIES_HD double rm_tan(double x) {
   const double g1 = 0x1.b096c00000000p-27, g2 = 0x1.f212d00000000p-5, g3 = 0x1.92f1a00000000p-1,
-               g4 = 25.0;
+               g4 = 25.0, g5 = 1.0e8;
   const double e0 = 0x1.5555555554dbdp-2, e1 = 0x1.11112e0a6b45fp-3;
   const double mp3 = -0x1.cb3b399d747f2p-55;
   uint32_t ux = (uint32_t)(RM_ASU(x) >> 32);
@@ -442,13 +443,25 @@ RIES_HD double rm_tan(double x) {
     double t2 = pz * (gi + fi) / (gi - pz);
     return s * (fi + t2);
   }
-  if (w <= g4) {
+  if (w <= g5) {
     double t = fma(x, RM_HPINV, RM_TOINT);
     double xn = t - RM_TOINT;
     int n = (int)(uint32_t)RM_ASU(t) & 1;
     double t1 = fma(-xn, RM_MP2, fma(-xn, RM_MP1, x));
-    double a = fma(-xn, mp3, t1);
-    double da = fma(-xn, mp3, t1 - a);
+    double a, da;
+    if (w <= g4) { /* |x| <= 25: one more term of pi/2 */
+      a = fma(-xn, mp3, t1);
+      da = fma(-xn, mp3, t1 - a);
+    } else { /* 25 < |x| <= 1e8: two more terms (pp3, pp4), then EADD(a, da) */
+      double tt = fma(-xn, RM_PP3, t1);
+      da = fma(-xn, RM_PP3, t1 - tt);
+      a = fma(-xn, RM_PP4, tt);
+      da = da + fma(-xn, RM_PP4, tt - a);
+      double z = a + da;
+      double zz = (fabs(a) > fabs(da)) ? ((a - z) + da) : ((da - z) + a);
+      a = z;
+      da = zz;
+    }
     double ya, yya, sy;
     if (a < 0.0) { ya = -a; yya = -da; sy = -1.0; }
     else { ya = a; yya = da; sy = 1.0; }
@@ -482,7 +495,7 @@ RIES_HD double rm_tan(double x) {
     double t2 = pz * (gi + fi) / (gi - pz);
     return sy * (fi + t2);
   }
-  return RM_NAN; /* |x| > 25: never reached from exec() (|a| <= pi) */
+  return RM_NAN; /* |x| > 1e8 (__branred range): never reached from exec(), |a| <= 100 pi */
 }
 
 /* ------------------------------------------------------------------------------------------

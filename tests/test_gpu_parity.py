@@ -46,6 +46,19 @@ def test_gpu_matches_live_reference_on_random_targets(product_lib, oracle_build)
         assert gpu_run(args) == run_binary(ref, args), t
 
 
+def test_gpu_matches_live_reference_on_random_command_lines(product_lib, oracle_build):
+    """Differential fuzz: seeded random combinations of the supported options and targets (tools/fuzz_cli.py)
+    through the GPU product and through the unmodified reference binary on this box."""
+    import sys
+    ref = os.path.join(oracle_build, "_ref", "ries")
+    if not os.path.exists(ref):
+        pytest.skip("no reference binary on this box")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_cli
+    for args in fuzz_cli.cases(40, 20261019):
+        assert gpu_run(args) == run_binary(ref, args), " ".join(args)
+
+
 def test_gpu_repeated_calls_are_independent(product_lib):
     """callMain may be called repeatedly on one module instance (ries.worker.js:64-123)."""
     a = gpu_run(["2.5063", "-l1", "-F3"])

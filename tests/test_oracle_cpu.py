@@ -41,6 +41,19 @@ def test_pass_fed_in_slices_prints_the_same(oracle_build, name):
     assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(name)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ries")), reason="no reference build")
+def test_random_command_lines_emulation_vs_reference(oracle_build):
+    """Differential fuzz of the host logic (argument parsing, set-up, replay, formatting) shared by the product:
+    seeded random option combinations through the emulation and through the unmodified reference."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_cli
+    ref = os.path.join(oracle_build, "_ref", "ries")
+    emu = os.path.join(oracle_build, "_build", "ries_emul")
+    for args in fuzz_cli.cases(25, 42):
+        assert run_binary(emu, args) == run_binary(ref, args), " ".join(args)
+
+
 def test_l4_headline_config(oracle_build):
     """BASELINE config 2 (ries 2.5063 -l4): emulation with rmath == unmodified reference, all 22 equations and
     every counter of the stats block."""
