@@ -9,6 +9,7 @@
 // replaying those candidates here in insertion order with the live threshold reproduces the
 // reference's streaming decisions exactly.
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -352,7 +353,8 @@ struct Search {
   double best_match = 0;
   bool got_exact = false;
   double num_matches = 0;
-  int lmin = 1, lmax = 1, rmin = 1, rmax = 1;
+  int16_t lmin = 1, lmax = 1, rmin = 1, rmax = 1; /* s16 in the reference (ries.c:3218): a search that never
+                                                    inserts anything ends by wrapping around, 12430/12445 */
 
   /* early-exit bookkeeping: which event of the running pass we are replaying */
   long resident_rows = 0;   /* rows inserted by completed passes */
@@ -885,8 +887,10 @@ struct Search {
       int using_x;
       int cplx;
       /* --one-sided: 'x' is the sole LHS expression, RHS passes from then on (ries.c:12425) */
-      if ((one_sided && st.lhs_insert >= 1) || (st.lhs_insert > st.rhs_insert)) { rmin++; rmax++; using_x = 0; cplx = rmax; }
-      else { lmin++; lmax++; using_x = 1; cplx = lmax; }
+      if ((one_sided && st.lhs_insert >= 1) || (st.lhs_insert > st.rhs_insert)) {
+        rmin = (int16_t)(rmin + 1); rmax = (int16_t)(rmax + 1); using_x = 0; cplx = rmax;
+      }
+      else { lmin = (int16_t)(lmin + 1); lmax = (int16_t)(lmax + 1); using_x = 1; cplx = lmax; }
       double genf = 0;
       double tf0 = now_sec();
       const std::vector<FormDesc>& forms = forms_for(cplx, &genf);

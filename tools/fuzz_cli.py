@@ -20,7 +20,7 @@ def target():
 
 def flags():
     f = []
-    f.append("-l%s" % rng.choice(["0", "1", "1", "2", "0.5", "-1"]))
+    f.append("-l%s" % rng.choice(os.environ.get("FUZZ_LEVELS", "0 1 1 2 0.5 -1").split()))
     if rng.random() < 0.7: f.append(rng.choice(["-F0", "-F1", "-F2", "-F3", "-F"]))
     if rng.random() < 0.25: f.append(rng.choice(["-i", "-r", "-a", "-c", "-ie", "-re", "-l"]))
     if rng.random() < 0.25: f.append("-N" + "".join(rng.sample(SYMS, rng.randint(1, 6))))
