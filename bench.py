@@ -297,7 +297,7 @@ def main():
     # N>1, default mode: after the independent-target steps, the same ranks also time ONE search together
     # (north_star's "time-to-full-report at -l6 on N GPUs"); reported beside the weak-scaling value
     sharded_extra = None
-    if dist is not None and not sharded:
+    if dist is not None and not sharded and os.environ.get("RIES_BENCH_NO_SHARDED_EXTRA") is None:
         join_search_communicator()
         sargv = [args.target, "-l" + args.level, "-F3", "--no-slow-messages"]
         for _ in range(2):
