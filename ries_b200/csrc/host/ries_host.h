@@ -64,6 +64,8 @@ struct Options {
   double derivative_margin = 0;       /* --derivative-margin (11284): 0 = automatic */
   double min_equ_val = -9.9e99, max_equ_val = 9.9e99; /* --min/--max-equate-value (11484, 11373) */
   double sincos_max_arg = 1.0;        /* --max-trig-cycles (11536) */
+  double trig_scale = 0;              /* --trig-argument-scale (11731): k_sincos_arg_scale, <= 0 means pi */
+  bool trig_scale_default = false;    /* g_trig_scale_default as parse_args leaves it */
   double sig_loss = 0.01;             /* --significance-loss-margin (11622) */
   bool match_all_digits = false;      /* --match-all-digits / --mad (11366) */
   bool explicit_multiply = false;     /* --explicit-multiply (11338) */
@@ -82,6 +84,7 @@ struct Options {
 /* State init2() + main()'s parameter set-up derive (ries.c:10314-10744, 12111-12317). */
 struct Setup {
   RiesParams P;
+  bool trig_pi_names = true; /* sinpi/cospi/tanpi vs sin/cos/tan (ries.c:10419-10441) */
   SymInfo info[RIES_MAX_SYMS];
   int idx_of[256]; /* char -> table index, -1 if unknown */
   double k_min_best_match;
@@ -101,7 +104,8 @@ void build_setup(Options& opt, Setup& S, const Sink& out);
 void finish_setup(Options& opt, Setup& S, const Sink& out);
 void show_symset(const Options& opt, const Setup& S, const Sink& out);
 void brief_help(const Sink& out);
-const char* sym_defn(unsigned char ch, bool normal);
+/* `pi_names`: the trig symbols are called sinpi/cospi/tanpi (k_sincos_arg_scale == k_pi, ries.c:10419) */
+const char* sym_defn(unsigned char ch, bool normal, bool pi_names = true);
 
 /* gen_forms/gf_1 + ge_1's suffix tables for one pass, in the reference's visiting order. */
 void gen_forms(const RiesParams& P, int e_minw, int e_maxw, std::vector<FormDesc>& forms,

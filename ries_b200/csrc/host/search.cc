@@ -507,9 +507,12 @@ struct Search {
   /* legend bookkeeping: defsym_used ries.c:7417, describe_symbols 7434-7516 */
   bool def_needed[256] = {false};
   bool def_given[256] = {false};
+  bool used_trig = false;
   void defsym_used(const std::string& e) {
-    for (size_t i = 0; i < e.size(); i++)
-      if (sym_defn((unsigned char)e[i], opt.out_format == OF_NORMAL)) def_needed[(unsigned char)e[i]] = true;
+    for (size_t i = 0; i < e.size(); i++) {
+      if (sym_defn((unsigned char)e[i], opt.out_format == OF_NORMAL, S.trig_pi_names)) def_needed[(unsigned char)e[i]] = true;
+      if (e[i] == 'C' || e[i] == 'S' || e[i] == 'T') used_trig = true;
+    }
   }
   void describe_symbols() {
     /* used_atan1/used_atan2 are only ever set by the infix formatter (6128-6133), so in postfix mode 'A' is
@@ -521,7 +524,7 @@ struct Search {
     bool normal = (opt.out_format == OF_NORMAL);
     auto defn = [&](int sym) -> const char* {
       if (sym == 0) return "atan2(s) = Angle of ray from origin through point (1,s)";
-      return sym_defn((unsigned char)sym, normal);
+      return sym_defn((unsigned char)sym, normal, S.trig_pi_names);
     };
     const int kLineLeftInit = 79 - 2;
     int lineleft = kLineLeftInit;
@@ -558,6 +561,12 @@ struct Search {
       }
     }
     if (lineleft < kLineLeftInit) out.printf("\n");
+    if (used_trig && !S.P.trig_scale_default) { /* 7501-7514 */
+      out.printf("  For the trig functions, ");
+      if (S.P.sincos_scale == 1.0) out.printf("2 pi");
+      else out.printf("%g", 2.0 * S.P.k_pi / S.P.sincos_scale);
+      out.printf(" units are a full circle.\n");
+    }
   }
 
   void check_exit(bool is_exact) { /* ries.c:7805 */

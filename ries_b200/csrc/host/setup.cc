@@ -81,8 +81,11 @@ static void set_restrict_alg(Options& o, int restrict_trig) { /* ries.c:10978 */
   somesyms_set(o, "^v", RIES_MAX_ELEN);
   o.restrict_exponents = TYPE_RAT;
   somesyms_set(o, "SCT", RIES_MAX_ELEN);
-  if (restrict_trig) o.restrict_trig_args = TYPE_RAT;
-  /* k_sincos_arg_scale = k_pi is already this build's only trig scale */
+  if (restrict_trig) {
+    o.restrict_trig_args = TYPE_RAT;
+    o.trig_scale = 3.14159265358979323846264338327950288419716; /* k_sincos_arg_scale = k_pi (static value, 3335) */
+    o.trig_scale_default = true;
+  }
 }
 
 /* parse_target ries.c:10758-10887 */
@@ -291,6 +294,24 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
         }
       } else {
         out.printf("%s: --max-trig-cycles should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--trig-argument-scale") == 0) { /* 11731 */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t) > 0) {
+        if ((t >= 0.0) && (t < 100.0)) {
+          o.trig_scale = t;
+          o.trig_scale_default = (t == 3.14159265358979323846264338327950288419716); /* k_pi's static value (3335) */
+          out.printf("Argument of trig functions will be scaled by %s\n", spfg(15, t).c_str());
+        } else {
+          out.printf("%s: --trig-argument-scale must be between 0.0 and 100.0\n\n", o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        }
+      } else {
+        out.printf("%s: --trig-argument-scale should be followed by a numeric argument.\n\n", o.argv0.c_str());
         brief_help(out);
         throw ExitRequest{-1};
       }
@@ -554,7 +575,12 @@ int guess_valtype(double v, int restrict_subexpr) {
 
 /* Symbol definitions for the legend / -S table: add_symbol's def_terse / def_normal arguments
    (ries.c:10375-10468). `normal` selects the -F2 wording. */
-const char* sym_defn(unsigned char ch, bool normal) {
+const char* sym_defn(unsigned char ch, bool normal, bool pi_names) {
+  if (!pi_names) { /* add_symbol(..., "S(x) = sine", 0, "sine") etc. (10436-10441): no -F2 definition */
+    if (ch == 'S') return normal ? 0 : "S(x) = sine";
+    if (ch == 'C') return normal ? 0 : "C(x) = cosine";
+    if (ch == 'T') return normal ? 0 : "T(x) = tangent";
+  }
   switch (ch) {
     case 'f': return normal ? "phi = the golden ratio, (1+sqrt(5))/2" : "f = phi, the golden ratio, (1+sqrt(5))/2";
     case 'e': return "e = base of natural logarithms, 2.71828...";
@@ -585,10 +611,12 @@ void show_symset(const Options& o, const Setup& S, const Sink& out) { /* ries.c:
       if (g < 0) continue;
       if (S.info[g].seft != seft || !S.info[g].alwd) continue;
       out.printf("  %c    %c   %2d   %-4s", i, S.info[g].seft, S.info[g].wgt, S.info[g].name_infix);
-      const char* def = sym_defn((unsigned char)i, o.out_format == OF_NORMAL);
+      const char* def = sym_defn((unsigned char)i, o.out_format == OF_NORMAL, S.trig_pi_names);
       if (def == 0) {
         for (int k = 0; k < kNumSymDefs; k++)
           if (kSymDefs[k].ch == (char)i) def = kSymDefs[k].desc;
+        if (!S.trig_pi_names && (i == 'S' || i == 'C' || i == 'T'))
+          def = (i == 'S') ? "sine" : (i == 'C') ? "cosine" : "tangent";
       }
       if (def) out.printf(" %s", def);
       out.printf("\n");
@@ -622,8 +650,11 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
     while (i > 1.0) { i -= 1.0; pi = 1.0 + (i / (1.0 + (2.0 * i))) * pi; }
     P.k_pi = 2.0 * pi;
   }
-  P.sincos_scale = P.k_pi; /* default trig scale (10158) */
-  P.trig_scale_default = 1;
+  /* init_numerics 10157-10161: an unset (<= 0) scale becomes pi and "default"; otherwise the flag is what
+     parse_args computed */
+  if (o.trig_scale <= 0) { P.sincos_scale = P.k_pi; P.trig_scale_default = 1; }
+  else { P.sincos_scale = o.trig_scale; P.trig_scale_default = o.trig_scale_default ? 1 : 0; }
+  S.trig_pi_names = (P.sincos_scale == P.k_pi);
   P.trig_max_arg = P.k_pi * o.sincos_max_arg; /* k_pi * k_sincos_max_arg (5503) */
   P.k_sin_clip = 0.99999;
   P.k_eXlim = 690.0;
@@ -667,6 +698,8 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
     S.info[g].alwd = P.sym_alwd[g];
     S.info[g].name_forth = d.forth;
     S.info[g].name_infix = d.infix;
+    if (!S.trig_pi_names && (d.ch == 'S' || d.ch == 'C' || d.ch == 'T')) /* 10436-10441 */
+      S.info[g].name_forth = S.info[g].name_infix = (d.ch == 'S') ? "sin" : (d.ch == 'C') ? "cos" : "tan";
     if (P.sym_alwd[g] != 0) {
       if (P.cls_n[cls] >= RIES_SLOTS) {
         out.printf("add_symbol: Too many seft '%c' symbols.\n", d.seft);
@@ -713,6 +746,13 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
       int g = S.idx_of[(unsigned char)kRules[r].sym];
       if (g >= 0) P.sym_mask[g] |= kRules[r].mask;
     }
+  }
+
+  if (P.sincos_scale == 1.0) { /* radians: [pS] => 0, [pC] => [1n] (10623-10628; no required symbols) */
+    int gs = S.idx_of[(unsigned char)'S'], gc = S.idx_of[(unsigned char)'C'];
+    if (gs >= 0) P.sym_mask[gs] |= AM_pi;
+    if (gc >= 0 && o.sa_alwd[(unsigned char)'1'] >= RIES_MAX_ELEN && o.sa_alwd[(unsigned char)'n'] >= RIES_MAX_ELEN)
+      P.sym_mask[gc] |= AM_pi;
   }
 
   /* g_exhaust_cpx (10669-10685), MAX_ELEN odd */

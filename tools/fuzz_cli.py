@@ -42,6 +42,8 @@ def flags():
     if rng.random() < 0.08: f += ["--derivative-margin", rng.choice(["1e-7", "1e-5", "1e-9"])]
     if rng.random() < 0.08: f += ["--max-equate-value", rng.choice(["10", "100"])]
     if rng.random() < 0.05: f += ["--numeric-anagram", "".join(rng.choice("123456789") for _ in range(rng.randint(2, 5)))]
+    if rng.random() < 0.06: f += ["--trig-argument-scale", rng.choice(["1", "0.0174532925199433", "2", "3.141592653589793", "0"])]
+    if rng.random() < 0.04: f += ["--symbol-weights", rng.choice(["8:T", "20:^", "14:x", "5:p"])]
     if rng.random() < 0.05: f.append("--no-canon-simplify")
     if rng.random() < 0.05: f += ["--any-exponents"]
     if rng.random() < 0.05: f += ["--rational-exponents"]
