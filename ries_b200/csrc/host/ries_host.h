@@ -69,6 +69,8 @@ struct Options {
   double sig_loss = 0.01;             /* --significance-loss-margin (11622) */
   bool match_all_digits = false;      /* --match-all-digits / --mad (11366) */
   bool explicit_multiply = false;     /* --explicit-multiply (11338) */
+  std::string sym_name[256];          /* --symbol-names (11648): sa_name = name_forth = given text */
+  bool sym_named[256];
   bool refinement = true;   /* --no-refinement (11577): the threshold never shrinks; every match inside it is printed once */
   bool one_sided = false;   /* --one-sided (11600): 'x' is the only LHS, RHS passes from then on (12425) */
   bool anagram = false;     /* --numeric-anagram (11586): digit budget through sa_alwd, implies one_sided */
@@ -84,7 +86,10 @@ struct Options {
 /* State init2() + main()'s parameter set-up derive (ries.c:10314-10744, 12111-12317). */
 struct Setup {
   RiesParams P;
-  bool trig_pi_names = true; /* sinpi/cospi/tanpi vs sin/cos/tan (ries.c:10419-10441) */
+  bool trig_pi_names = true;
+  std::string name_store[256]; /* owns the --symbol-names strings the SymInfo pointers refer to */
+  const char* any_name[256];   /* sa_name of every character code, symbol or not ('=', '(', '.', ...) */
+  const char* any_forth[256];  /* name_forth of every character code (0 = none) */ /* sinpi/cospi/tanpi vs sin/cos/tan (ries.c:10419-10441) */
   SymInfo info[RIES_MAX_SYMS];
   int idx_of[256]; /* char -> table index, -1 if unknown */
   double k_min_best_match;

@@ -316,10 +316,7 @@ std::string infix_expand(const InfixCtx& cx, const std::string& in) {
   for (size_t i = 0; i < in.size(); i++) {
     unsigned char c = (unsigned char)in[i];
     switch (c) {
-      case '(': o += "("; break;
-      case ',': o += ","; break;
-      case ')': o += ")"; break;
-      case '=': o += "="; break;
+      case '(': case ',': case ')': case '=': o += cx.S->any_name[c]; break;
       case '.': o += " "; break;
       default: {
         int g = cx.S->idx_of[c];
@@ -740,7 +737,7 @@ struct Search {
     if (justify_overflow < 0) justify_overflow = 0;
 
     std::string line(l_pad, ' ');
-    line += " " + l_fmt + " = " + r_fmt + " ";
+    line += " " + l_fmt + " " + S.any_name[(unsigned char)'='] + " " + r_fmt + " ";
     line.append(r_pad, ' ');
 
     std::string froot = spfg(S.k_usable_digits, root);

@@ -29,7 +29,7 @@ void Sink::printf(const char* fmt, ...) const {
 
 /* init1(): every symbol allowed MAX_ELEN times except W (ries.c:10262-10266) */
 Options::Options() {
-  for (int i = 0; i < 256; i++) { sa_alwd[i] = RIES_MAX_ELEN; preempt_weight[i] = -1; }
+  for (int i = 0; i < 256; i++) { sa_alwd[i] = RIES_MAX_ELEN; preempt_weight[i] = -1; sym_named[i] = false; }
   sa_alwd[(unsigned char)'W'] = 0;
 }
 
@@ -351,6 +351,37 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       } else {
         out.printf("%s: --numeric-anagram should be followed by a string of digits.\n\n", o.argv0.c_str());
         brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--symbol-names") == 0) { /* ries.c:11648 */
+      if (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
+        char space_sym = ' ';
+        while (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
+          const char* arg = next_arg();
+          if ((arg[0] == ':') && arg[1] && (arg[2] == ':') && (arg[3] == arg[1]) && (arg[4] == 0) && (space_sym == ' ')) {
+            space_sym = arg[1]; /* :c:c defines the character that stands for a blank */
+          } else if ((arg[0] == ':') && arg[1] && (arg[2] == ':')) {
+            if (strlen(arg + 3) <= 24) {
+              std::string nm(arg + 3);
+              for (size_t k = 0; k < nm.size(); k++)
+                if (nm[k] == space_sym) nm[k] = ' ';
+              o.sym_name[(unsigned char)arg[1]] = nm;
+              o.sym_named[(unsigned char)arg[1]] = true;
+            } else {
+              out.printf("%s: Symbol name can be at most %d characters\n(I got '%s')\n", o.argv0.c_str(), 24, arg + 3);
+              throw ExitRequest{-1};
+            }
+          } else {
+            out.printf("%s: --symbol-names argument syntax is :<sym>:name, for example\n"
+                       "  :-:deme   to set name of '-' to 'deme'\n"
+                       "  Instead I got '%s'\n", o.argv0.c_str(), arg);
+            throw ExitRequest{-1};
+          }
+        }
+      } else {
+        out.printf("%s: --symbol-names should be followed by one or more tuples\n"
+                   "  of the form <sym>:name, for example:\n"
+                   "  :-:deme   to set name of '-' to 'deme'\n", o.argv0.c_str());
         throw ExitRequest{-1};
       }
     } else if (strcmp(a, "--symbol-weights") == 0) { /* ries.c:11689 */
@@ -678,6 +709,21 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
     throw ExitRequest{1};
   }
 
+  /* the infix punctuation, which --symbol-names can rename too (10481-10485) */
+  for (int c = 0; c < 256; c++) { S.any_name[c] = 0; S.any_forth[c] = 0; }
+  S.any_name[(unsigned char)'('] = "("; S.any_name[(unsigned char)','] = ",";
+  S.any_name[(unsigned char)')'] = ")"; S.any_name[(unsigned char)'='] = "=";
+  {
+    const char* punct = "(,)=";
+    for (const char* q = punct; *q; q++) {
+      unsigned char c = (unsigned char)*q;
+      if (o.sym_named[c] && !o.sym_name[c].empty()) {
+        S.name_store[c] = o.sym_name[c];
+        S.any_name[c] = S.name_store[c].c_str();
+      }
+    }
+  }
+
   /* symbol table */
   P.nsym = kNumSymDefs;
   for (int g = 0; g < kNumSymDefs; g++) {
@@ -700,6 +746,14 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
     S.info[g].name_infix = d.infix;
     if (!S.trig_pi_names && (d.ch == 'S' || d.ch == 'C' || d.ch == 'T')) /* 10436-10441 */
       S.info[g].name_forth = S.info[g].name_infix = (d.ch == 'S') ? "sin" : (d.ch == 'C') ? "cos" : "tan";
+    if (o.sym_named[(unsigned char)d.ch]) {
+      /* --symbol-names set sa_name = name_forth = the text; add_symbol keeps a non-empty user name and
+         otherwise installs its defaults (9855-9862) */
+      S.name_store[(unsigned char)d.ch] = o.sym_name[(unsigned char)d.ch];
+      const char* given = S.name_store[(unsigned char)d.ch].c_str();
+      if (given[0]) { S.info[g].name_infix = given; S.info[g].name_forth = given; }
+      else if (S.info[g].name_forth == 0) S.info[g].name_forth = given; /* the empty string stays */
+    }
     if (P.sym_alwd[g] != 0) {
       if (P.cls_n[cls] >= RIES_SLOTS) {
         out.printf("add_symbol: Too many seft '%c' symbols.\n", d.seft);
