@@ -147,6 +147,54 @@ RIES_HD unsigned expand_mask(const RiesParams& P, const TestTables& T, const For
   return m;
 }
 
+/* canonval (ries.c:8753-8892): after a complete expression has passed every prune, up to four more
+   operators are appended so that its value moves towards [1,2): [n] when negative, [r] when |v| < 1,
+   [2/] when |v| >= 2, [2*] when |v| < 1 -- each only if its symbols may still be used (sa_ct < sa_alwd,
+   the counts being those of the expression before canonval touched it) and the longer expression fits
+   MAX_ELEN.  `r` is updated in place; the returned code (bit per operator, same bits as canon_ops) tells
+   expand_finish() which symbols to append.  An exec() error abandons the expression uncounted (9145-9151;
+   the reference also leaves its metastack one undo short there -- no search reaches that case: 1/v of
+   a value that has passed the prunes, v/2 and v*2 do not fail). */
+enum { CANON_NEG = 1, CANON_RECIP = 2, CANON_DIV2 = 4, CANON_MUL2 = 8 };
+
+RIES_HD bool canon_may_use(const RiesParams& P, int which, const Sym128& sym, int len) {
+  const int g = P.canon_sym[which];
+  if (g < 0) return false;
+  const int alwd = P.sym_alwd[g];
+  if (alwd >= RIES_MAX_ELEN) return true;
+  int ct = 0;
+  for (int i = 0; i < len; i++) ct += (sym_get(sym, i) == (unsigned)(g + 1));
+  return ct < alwd;
+}
+
+RIES_HD int canon_apply(const RiesParams& P, bool do_dx, const Sym128& sym, int len, Val& r, int& code) {
+  int ip = len;
+  code = 0;
+  Val t;
+  if ((P.canon_ops & CANON_NEG) && canon_may_use(P, 0, sym, len) && (r.v < 0.0) && (ip < RIES_MAX_ELEN)) {
+    if (exec_unary(P, 'n', do_dx, r, t)) return 1;
+    r = t; ip += 1; code |= CANON_NEG;
+  }
+  if ((P.canon_ops & CANON_RECIP) && canon_may_use(P, 1, sym, len) && (r.v * r.v < 1.0) && (ip < RIES_MAX_ELEN)) {
+    if (exec_unary(P, 'r', do_dx, r, t)) return 1;
+    r = t; ip += 1; code |= CANON_RECIP;
+  }
+  if ((P.canon_ops & (CANON_DIV2 | CANON_MUL2)) && canon_may_use(P, 2, sym, len)) {
+    Val two;
+    if ((P.canon_ops & CANON_DIV2) && canon_may_use(P, 3, sym, len) && (r.v * r.v >= 4.0) && (ip + 1 < RIES_MAX_ELEN)) {
+      if (exec_push(P, '2', P.target, two)) return 1;
+      if (exec_binary(P, '/', do_dx, r, two, t)) return 1;
+      r = t; ip += 2; code |= CANON_DIV2;
+    }
+    if ((P.canon_ops & CANON_MUL2) && canon_may_use(P, 4, sym, len) && (r.v * r.v < 1.0) && (ip + 1 < RIES_MAX_ELEN)) {
+      if (exec_push(P, '2', P.target, two)) return 1;
+      if (exec_binary(P, '*', do_dx, r, two, t)) return 1;
+      r = t; ip += 2; code |= CANON_MUL2;
+    }
+  }
+  return 0;
+}
+
 /* exec of the chosen symbol on the cactus stack (the child's ge_2 entry, 8942-8954), the value prunes
    (8962-9076) and the complete-expression tests (9085-9139).  `nodes` is the pass's node arena
    (parents of every level stay resident for `below` links); `par_idx` is the parent's own index.
@@ -188,28 +236,52 @@ RIES_HD int expand_exec(const RiesParams& P, int cls, int g, bool complete, cons
     if ((r.d != 0.0) && (fabs(r.d) / (1.0 + fabs(r.v)) < P.k_vanished_dx)) return OUT_DEAD;
     if ((sp == 1) && (fabs(r.d) / (1.0 + fabs(r.v)) < P.k_vanished_dx)) return OUT_DEAD;
   }
-  child.val = r.v;
-  child.der = r.d;
-  child.tag = (uint8_t)r.tag;
-  child.below = below;
-  child.sp = (uint8_t)sp;
+  child.pad0 = 0;
   if (complete) {
     /* complete expression (9085-9139) */
     if (using_x && (fabs(r.d) < P.k_vanished_dx)) return OUT_DEAD;
     if (r.v < P.min_equ_val) return OUT_DEAD;
     if (r.v > P.max_equ_val) return OUT_DEAD;
-    return OUT_DONE;
+    if (P.canon_ops) {
+      /* the value the table sees is the canonical one (9144); pad0 carries which symbols to append */
+      Sym128 full = par.sym;
+      sym_set(full, par.len, (unsigned)(g + 1));
+      int code;
+      if (canon_apply(P, using_x != 0, full, par.len + 1, r, code)) return OUT_ERR;
+      child.pad0 = (uint8_t)code;
+    }
   }
-  return OUT_LIVE;
+  child.val = r.v;
+  child.der = r.d;
+  child.tag = (uint8_t)r.tag;
+  child.below = below;
+  child.sp = (uint8_t)sp;
+  return complete ? OUT_DONE : OUT_LIVE;
 }
 
-/* The bookkeeping part of a child: symbols, form, complexity, length. */
+/* The bookkeeping part of a child: symbols, form, complexity, length.  child.pad0 is canon_apply's code
+   (nonzero only for complete expressions under --canon-reduction): its symbols are appended here; the
+   complexity stays that of the expression as enumerated (canonval leaves bpe->cplx alone). */
 RIES_HD void expand_finish(const RiesParams& P, const Node& par, int g, Node& child) {
   child.sym = par.sym;
   sym_set(child.sym, par.len, (unsigned)(g + 1));
   child.form = par.form;
   child.cplx = (int16_t)(par.cplx + P.sym_wgt[g]);
-  child.len = (uint8_t)(par.len + 1);
+  int len = par.len + 1;
+  const int code = child.pad0;
+  if (code) {
+    if (code & CANON_NEG) sym_set(child.sym, len++, (unsigned)(P.canon_sym[0] + 1));
+    if (code & CANON_RECIP) sym_set(child.sym, len++, (unsigned)(P.canon_sym[1] + 1));
+    if (code & CANON_DIV2) {
+      sym_set(child.sym, len++, (unsigned)(P.canon_sym[2] + 1));
+      sym_set(child.sym, len++, (unsigned)(P.canon_sym[3] + 1));
+    }
+    if (code & CANON_MUL2) {
+      sym_set(child.sym, len++, (unsigned)(P.canon_sym[2] + 1));
+      sym_set(child.sym, len++, (unsigned)(P.canon_sym[4] + 1));
+    }
+  }
+  child.len = (uint8_t)len;
   child.pad0 = 0;
   child.pad1 = 0;
 }

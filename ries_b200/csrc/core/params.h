@@ -118,6 +118,10 @@ struct RiesParams {
   int restrict_subexpr, restrict_exponents, restrict_trig_args;
   int trig_scale_default;
   int no_cv_simplify;
+  /* --canon-reduction (g_canon_ops, ries.c:8728-8732): bit 0 negate, 1 reciprocal, 2 divide by 2, 3 multiply
+     by 2; canon_sym[] = dense indices of 'n' 'r' '2' '/' '*' (what canonval appends, 8786-8875) */
+  int canon_ops;
+  signed char canon_sym[8];
 };
 
 /* One a/b/c form of a pass (gf_1 ries.c:9599-9767 + ge_1's suffix tables 9535-9566). */

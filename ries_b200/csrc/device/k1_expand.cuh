@@ -203,7 +203,7 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
             else if (oc == OUT_LIVE || oc == OUT_DONE) {
               Staged st;
               st.val = child.val; st.der = child.der; st.below = child.below; st.tag = child.tag; st.sp = child.sp;
-              st.pad0 = 0; st.pad1 = 0;
+              st.pad0 = child.pad0; st.pad1 = 0; /* pad0: canon_apply's code */
               staged[i] = st;
               if (oc == OUT_LIVE) { atomicOr(&B.live[pl], 1u << k); B.item[i] = (unsigned short)(it | IT_LIVE); }
               else { atomicOr(&B.done[pl], 1u << k); B.item[i] = (unsigned short)(it | IT_DONE); }
@@ -257,6 +257,7 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
           const Staged st = staged[i];
           Node child;
           child.val = st.val; child.der = st.der; child.below = st.below; child.tag = st.tag; child.sp = st.sp;
+          child.pad0 = st.pad0;
           expand_finish(P, par, g, child);
           const u32 below_k = (1u << k) - 1;
           if (it & IT_LIVE) {

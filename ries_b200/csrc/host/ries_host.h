@@ -60,6 +60,7 @@ struct Options {
   bool NOS_options = false;
   bool allow_slow_message = true;
   bool no_cv_simplify = false;
+  int canon_ops = 0; /* --canon-reduction (ries.c:11255): CANONVAL_* bits */
   bool solve_for_x = false; /* -s / --try-solve-for-x (ries.c:11756) */
   double derivative_margin = 0;       /* --derivative-margin (11284): 0 = automatic */
   double min_equ_val = -9.9e99, max_equ_val = 9.9e99; /* --min/--max-equate-value (11484, 11373) */

@@ -157,6 +157,21 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       break;
     } else if (strcmp(a, "-") == 0) {
       /* null option */
+    } else if (strcmp(a, "--canon-reduction") == 0) { /* ries.c:11255 */
+      if (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
+        const char* v = next_arg();
+        o.canon_ops = 0;
+        for (; *v; v++) {
+          if (*v == 'n') o.canon_ops |= 1;       /* CANONVAL_NEGATE */
+          else if (*v == 'r') o.canon_ops |= 2;  /* CANONVAL_RECIPROCAL */
+          else if (*v == '5') o.canon_ops |= 4;  /* CANONVAL_DIV2 */
+          else if (*v == '2') o.canon_ops |= 8;  /* CANONVAL_MUL2 */
+        }
+      } else {
+        out.printf("%s: --canon-reduction requires a set of reduction types, e.g. 'nr25'\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
     } else if (strcmp(a, "--canon-simplify") == 0) {
       o.no_cv_simplify = false;
     } else if (strcmp(a, "--no-canon-simplify") == 0) {
@@ -697,6 +712,7 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
   P.tg_e = TYPE_TCEL;
   P.tg_pi = TYPE_TCEL;
   P.no_cv_simplify = o.no_cv_simplify ? 1 : 0;
+  P.canon_ops = o.canon_ops;
 
   /* -Nx is prohibited; -Ox means "x once, LHS only" (10336-10340) */
   if (o.sa_alwd[(unsigned char)'x'] == 1) S.x_lhs_only = true;
@@ -726,9 +742,11 @@ void build_setup(Options& o, Setup& S, const Sink& out) {
 
   /* symbol table */
   P.nsym = kNumSymDefs;
+  for (int k = 0; k < 8; k++) P.canon_sym[k] = -1;
   for (int g = 0; g < kNumSymDefs; g++) {
     const SymDef& d = kSymDefs[g];
     int cls = d.seft - 'a';
+    { const char* cs = "nr2/*"; const char* at = strchr(cs, d.ch); if (d.ch && at) P.canon_sym[at - cs] = (signed char)g; }
     P.sym_char[g] = (unsigned char)d.ch;
     P.sym_cls[g] = (unsigned char)cls;
     /* base complexity 10 + per-symbol weight, unless --symbol-weights overrides it (ries.c:9872) */

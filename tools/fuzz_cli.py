@@ -45,6 +45,7 @@ def flags():
     if rng.random() < 0.06: f += ["--trig-argument-scale", rng.choice(["1", "0.0174532925199433", "2", "3.141592653589793", "0"])]
     if rng.random() < 0.04: f += ["--symbol-weights", rng.choice(["8:T", "20:^", "14:x", "5:p"])]
     if rng.random() < 0.05: f.append("--no-canon-simplify")
+    if rng.random() < 0.12: f += ["--canon-reduction", rng.choice(["nr25", "n", "r", "2", "5", "nr", "25", "r5", "n2", "0"])]
     if rng.random() < 0.05: f += ["--any-exponents"]
     if rng.random() < 0.05: f += ["--rational-exponents"]
     rng.shuffle(f)
