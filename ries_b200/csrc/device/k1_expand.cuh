@@ -13,7 +13,14 @@
 #ifndef EXP_THREADS
 #define EXP_THREADS 256
 #endif
-#define EXP_PARENTS EXP_THREADS
+/* live prefixes per thread and tile: a tile of EXP_PPT x EXP_THREADS prefixes yields ~1.3 x that many
+   (prefix, symbol) pairs, i.e. more 32-pair batches per warp in phase 3 (less waiting for the last batch)
+   and fewer block barriers per prefix */
+#ifndef EXP_PPT
+#define EXP_PPT 1
+#endif
+#define EXP_PARENTS (EXP_PPT * EXP_THREADS)
+#define EXP_VWARPS (EXP_PARENTS / 32)
 #define EXP_MAX_ITEMS (EXP_PARENTS * RIES_SLOTS)
 #ifndef EXP_MIN_BLOCKS
 #define EXP_MIN_BLOCKS 3
@@ -84,38 +91,58 @@ struct TileBuf {
 
 #define EXP_DYN_SMEM (2 * sizeof(TileBuf))
 
-__global__ void __launch_bounds__(EXP_THREADS, EXP_MIN_BLOCKS)
-k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+/* One expression position of the running pass.  TINY = called by the first EXP_THREADS threads of the
+   1024-thread single-block kernel k_tiny_front (which loops over the positions itself): the block barrier is
+   then a named barrier over those threads only. */
+template <bool TINY>
+__device__ __forceinline__ void exp_sync() {
+  if (TINY) asm volatile("bar.sync 1, %0;" ::"n"(EXP_THREADS) : "memory");
+  else __syncthreads();
+}
+
+/* TINY (single block, see tiny_pass.cuh): no other block exists, so the tile ticket, the published tile
+   aggregates, the look-back and the last-block election -- each a dependent round trip to L2 -- are replaced
+   by a loop counter and running sums in shared memory, the search constants are loaded once per pass
+   (`first`), and the frontier bounds travel in shared memory (s_lvl) instead of the control block. */
+template <bool TINY>
+__device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl,
+                                             const bool first = true) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   TileBuf* s_buf = (TileBuf*)s_dyn; /* [2] */
   __shared__ u32 s_opcnt[RIES_MAX_SYMS];
   __shared__ RiesParams P;
   __shared__ TestTables TT;
-  __shared__ u32 s_wcnt[EXP_THREADS / 32][RIES_SLOTS];
+  __shared__ u32 s_wcnt[EXP_VWARPS][RIES_SLOTS];
   __shared__ u32 s_slot_base[RIES_SLOTS];
-  __shared__ u32 s_wl[EXP_THREADS / 32], s_wd[EXP_THREADS / 32];
+  __shared__ u32 s_wl[EXP_VWARPS], s_wd[EXP_VWARPS];
   __shared__ u32 s_live_base, s_done_base, s_dead, s_tile, s_last, s_next;
+  __shared__ u32 s_run_live, s_run_done; /* TINY: children appended by the tiles before the current one */
+  __shared__ u32 s_lvl[4];               /* TINY: lvl_begin, lvl_end, done_count, overflow */
 
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const u32 lvl_begin = ctl->lvl_begin, lvl_end = ctl->lvl_end;
+  if (TINY && first) {
+    if (tid == 0) { s_lvl[0] = ctl->lvl_begin; s_lvl[1] = ctl->lvl_end; s_lvl[2] = ctl->done_count; s_lvl[3] = ctl->overflow; }
+    exp_sync<TINY>();
+  }
+  const u32 lvl_begin = TINY ? s_lvl[0] : ctl->lvl_begin, lvl_end = TINY ? s_lvl[1] : ctl->lvl_end;
   const u32 n = lvl_end - lvl_begin;
   const u32 ntiles = (n + EXP_PARENTS - 1) / EXP_PARENTS;
   const DevPtrs D = *Dp;
   const int using_x = Ap->using_x, cplx = Ap->cplx;
   const u32 cap_nodes = Ap->cap_nodes, cap_done = Ap->cap_done;
-  if (ntiles != 0 && !(ctl->overflow & (OVF_NODES | OVF_DONE))) {
-    {
+  if (ntiles != 0 && !((TINY ? s_lvl[3] : ctl->overflow) & (OVF_NODES | OVF_DONE))) {
+    if (!TINY || first) {
       const u32* src = (const u32*)D.P;
       u32* dst = (u32*)&P;
       for (u32 i = tid; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];
       const u32* tsrc = (const u32*)D.tt;
       u32* tdst = (u32*)&TT;
       for (u32 i = tid; i < sizeof(TestTables) / 4; i += EXP_THREADS) tdst[i] = tsrc[i];
-      if (tid == 0) s_dead = 0;
-      if (tid < RIES_MAX_SYMS) s_opcnt[tid] = 0;
     }
-    __syncthreads();
-    const u32 done_base0 = ctl->done_count; /* read-only during the tile loop (updated by the last block) */
+    if (tid == 0) { s_dead = 0; s_run_live = 0; s_run_done = 0; }
+    if (tid < RIES_MAX_SYMS) s_opcnt[tid] = 0;
+    exp_sync<TINY>();
+    const u32 done_base0 = TINY ? s_lvl[2] : ctl->done_count; /* read-only during the tile loop (updated by the last block) */
     const u32 lt = (1u << lane) - 1;
     Node* nodes = D.nodes;
     const FormDesc* forms = D.forms;
@@ -123,65 +150,77 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
     u32 my_dead = 0;
     int cur = 0;
     bool have_prev = false;
+    u32 tiny_tile = 0;
 
     /* Tiles are handed out by ticket, so a tile's predecessors (which its look-back waits on) are always
        held by blocks that are already running: safe even when not every block of the grid is resident
        (several engines sharing the GPU on different streams).  The loop is software-pipelined: the front
        half of tile t+1 runs between the publication of tile t's aggregate and t's look-back. */
     while (true) {
-      if (tid == 0) { s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next = 0; }
-      __syncthreads();
-      const u32 tile = s_tile;
+      if (tid == 0) { if (!TINY) s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next = 0; }
+      exp_sync<TINY>();
+      const u32 tile = TINY ? tiny_tile++ : s_tile;
       const bool have_cur = tile < ntiles;
       if (have_cur) {
         TileBuf& B = s_buf[cur];
         Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + cur) * EXP_MAX_ITEMS;
         const u32 p0 = lvl_begin + tile * EXP_PARENTS;
         /* ---- phase 1: integer tests, one thread per prefix ---- */
-        u32 mask = 0;
-        {
-          const u32 p = p0 + tid;
+        u32 mask[EXP_PPT];
+#pragma unroll
+        for (int j = 0; j < EXP_PPT; j++) {
+          const u32 pl = (u32)j * EXP_THREADS + tid;
+          const u32 p = p0 + pl;
+          mask[j] = 0;
           if (p < lvl_end) {
             const Node par = nodes[p];
-            B.par[tid] = par;
+            B.par[pl] = par;
             const FormDesc& F = forms[par.form];
             const int cls = F.cls[par.len];
             const int ns = P.cls_n[cls];
             const int atts = prefix_attrs(P, F, par, using_x);
-            mask = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
-            my_dead += (u32)ns - (u32)__popc(mask);
-            B.cls[tid] = (unsigned char)cls;
-            B.complete[tid] = (unsigned char)(par.len + 1 >= F.flen);
+            mask[j] = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
+            my_dead += (u32)ns - (u32)__popc(mask[j]);
+            B.cls[pl] = (unsigned char)cls;
+            B.complete[pl] = (unsigned char)(par.len + 1 >= F.flen);
           }
-          B.live[tid] = 0;
-          B.done[tid] = 0;
+          B.live[pl] = 0;
+          B.done[pl] = 0;
         }
         /* ---- phase 2: list the surviving pairs grouped by slot ---- */
 #pragma unroll
-        for (int k = 0; k < RIES_SLOTS; k++) {
-          u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-          if (lane == 0) s_wcnt[warp][k] = __popc(b);
+        for (int j = 0; j < EXP_PPT; j++) {
+#pragma unroll
+          for (int k = 0; k < RIES_SLOTS; k++) {
+            u32 b = __ballot_sync(0xffffffffu, (mask[j] >> k) & 1u);
+            if (lane == 0) s_wcnt[j * (EXP_THREADS / 32) + warp][k] = __popc(b);
+          }
         }
-        __syncthreads();
-        if (tid < RIES_SLOTS) { /* per slot: exclusive prefix over warps, and the slot's total */
+        exp_sync<TINY>();
+        if (tid < RIES_SLOTS) { /* per slot: exclusive prefix over (virtual) warps, and the slot's total */
           u32 run = 0;
-          for (int w = 0; w < EXP_THREADS / 32; w++) { u32 c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+          for (int w = 0; w < EXP_VWARPS; w++) { u32 c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
           s_slot_base[tid] = run;
         }
-        __syncthreads();
+        exp_sync<TINY>();
         if (tid == 0) {
           u32 run = 0;
           for (int k = 0; k < RIES_SLOTS; k++) { u32 c = s_slot_base[k]; s_slot_base[k] = run; run += c; }
           B.total = run;
           B.tile = tile;
         }
-        __syncthreads();
+        exp_sync<TINY>();
 #pragma unroll
-        for (int k = 0; k < RIES_SLOTS; k++) {
-          u32 b = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-          if ((mask >> k) & 1u) B.item[s_slot_base[k] + s_wcnt[warp][k] + __popc(b & lt)] = (unsigned short)((tid << 4) | k);
+        for (int j = 0; j < EXP_PPT; j++) {
+          const u32 pl = (u32)j * EXP_THREADS + tid;
+#pragma unroll
+          for (int k = 0; k < RIES_SLOTS; k++) {
+            u32 b = __ballot_sync(0xffffffffu, (mask[j] >> k) & 1u);
+            if ((mask[j] >> k) & 1u)
+              B.item[s_slot_base[k] + s_wcnt[j * (EXP_THREADS / 32) + warp][k] + __popc(b & lt)] = (unsigned short)((pl << 4) | k);
+          }
         }
-        __syncthreads();
+        exp_sync<TINY>();
         const u32 T = B.total;
         /* ---- phase 3: exec + value prunes; warps pull 32 listed pairs at a time (a warp's batch is
            almost always one operator, and heavy operators spread over the warps) ---- */
@@ -193,7 +232,7 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
           const u32 i = b0 + lane;
           if (i < T) {
             const u32 it = B.item[i];
-            const u32 pl = it >> 4, k = it & 15u;
+            const u32 pl = (it >> 4) & 1023u, k = it & 15u;
             const int cls = B.cls[pl];
             const int g = P.trial[cls][k];
             Node child;
@@ -210,28 +249,37 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
             }
           }
         }
-        __syncthreads();
+        exp_sync<TINY>();
         /* child offsets inside the tile, and the tile's aggregate -> published at once */
         {
-          u32 nl = __popc(B.live[tid]), nd = __popc(B.done[tid]);
-          u32 il = nl, id = nd;
-          for (int o = 1; o < 32; o <<= 1) {
-            u32 a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, id, o);
-            if (lane >= (u32)o) { il += a; id += b; }
+          u32 xl[EXP_PPT], xd[EXP_PPT]; /* exclusive offsets inside the (virtual) warp */
+#pragma unroll
+          for (int j = 0; j < EXP_PPT; j++) {
+            const u32 pl = (u32)j * EXP_THREADS + tid;
+            u32 nl = __popc(B.live[pl]), nd = __popc(B.done[pl]);
+            u32 il = nl, id = nd;
+            for (int o = 1; o < 32; o <<= 1) {
+              u32 a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, id, o);
+              if (lane >= (u32)o) { il += a; id += b; }
+            }
+            if (lane == 31) { s_wl[j * (EXP_THREADS / 32) + warp] = il; s_wd[j * (EXP_THREADS / 32) + warp] = id; }
+            xl[j] = il - nl; xd[j] = id - nd;
           }
-          if (lane == 31) { s_wl[warp] = il; s_wd[warp] = id; }
-          __syncthreads();
-          u32 wl = 0, wd = 0, la = 0, da = 0;
-          for (u32 w = 0; w < EXP_THREADS / 32; w++) {
-            const u32 a = s_wl[w], b = s_wd[w];
-            if (w < warp) { wl += a; wd += b; }
-            la += a; da += b;
+          exp_sync<TINY>();
+          u32 la = 0, da = 0;
+          for (u32 w = 0; w < EXP_VWARPS; w++) { la += s_wl[w]; da += s_wd[w]; }
+#pragma unroll
+          for (int j = 0; j < EXP_PPT; j++) {
+            const u32 vw = (u32)j * (EXP_THREADS / 32) + warp;
+            const u32 pl = (u32)j * EXP_THREADS + tid;
+            u32 wl = 0, wd = 0;
+            for (u32 w = 0; w < vw; w++) { wl += s_wl[w]; wd += s_wd[w]; }
+            B.lbase[pl] = wl + xl[j];
+            B.dbase[pl] = wd + xd[j];
           }
-          B.lbase[tid] = wl + il - nl;
-          B.dbase[tid] = wd + id - nd;
           if (tid == 0) {
             B.live_agg = la; B.done_agg = da;
-            tile_publish(tile_state, tile, la, da);
+            if (!TINY) tile_publish(tile_state, tile, la, da);
           }
         }
       }
@@ -239,12 +287,17 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
       if (have_prev) {
         TileBuf& B = s_buf[cur ^ 1];
         const Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * EXP_MAX_ITEMS;
-        if (warp == 0) {
+        if (TINY) {
+          if (tid == 0) {
+            s_live_base = s_run_live; s_done_base = s_run_done;
+            s_run_live += B.live_agg; s_run_done += B.done_agg;
+          }
+        } else if (warp == 0) {
           u32 le, de;
           tile_lookback(tile_state, B.tile, B.live_agg, B.done_agg, le, de);
           if (lane == 0) { s_live_base = le; s_done_base = de; }
         }
-        __syncthreads();
+        exp_sync<TINY>();
         const u32 T = B.total;
         const u32 p_tile = B.tile;
         (void)p_tile;
@@ -273,7 +326,7 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
           }
         }
       }
-      __syncthreads(); /* s_tile, s_live_base and the buffers are reused by the next round */
+      exp_sync<TINY>(); /* s_tile, s_live_base and the buffers are reused by the next round */
       if (!have_cur) break;
       have_prev = true;
       cur ^= 1;
@@ -281,23 +334,48 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
     /* block-level dead-end count -> one atomic per block */
     for (int o = 16; o > 0; o >>= 1) my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
     if (lane == 0 && my_dead) atomicAdd(&s_dead, my_dead);
-    __syncthreads();
+    exp_sync<TINY>();
     if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
     if (tid < RIES_MAX_SYMS && s_opcnt[tid]) atomicAdd(&D.opcnt[(using_x ? RIES_MAX_SYMS : 0) + tid], (u64)s_opcnt[tid]);
   }
 
+  if (TINY) {
+    /* level finish, single block: same bookkeeping, no election, no tile states to clear */
+    exp_sync<TINY>();
+    if (tid == 0) {
+      u32 ovf = s_lvl[3];
+      if (!(ovf & (OVF_NODES | OVF_DONE))) {
+        const u32 live = ntiles ? s_run_live : 0, dn = ntiles ? s_run_done : 0;
+        u64 new_nodes = (u64)lvl_end + live;
+        u64 new_done = (u64)s_lvl[2] + dn;
+        if (new_nodes > cap_nodes) ovf |= OVF_NODES;
+        if (new_done > cap_done) ovf |= OVF_DONE;
+        s_lvl[3] = ovf;
+        s_lvl[0] = lvl_end;
+        s_lvl[1] = (ovf & (OVF_NODES | OVF_DONE)) ? lvl_end : (u32)new_nodes;
+        s_lvl[2] = (new_done > 0xffffffffull) ? 0xffffffffu : (u32)new_done;
+        if (ovf) atomicOr(&ctl->overflow, ovf);
+        ctl->lvl_begin = s_lvl[0];
+        ctl->lvl_end = s_lvl[1];
+        ctl->node_count = (new_nodes > 0xffffffffull) ? 0xffffffffu : (u32)new_nodes;
+        ctl->done_count = s_lvl[2];
+      }
+    }
+    exp_sync<TINY>();
+    return;
+  }
   /* ---- level finish by the last block to get here (replaces a separate launch) ---- */
-  __syncthreads();
+  exp_sync<TINY>();
   if (tid == 0) {
     __threadfence();
     s_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
   }
-  __syncthreads();
+  exp_sync<TINY>();
   if (!s_last) return;
   __threadfence();
   volatile u64* tile_state = (volatile u64*)D.tiles;
   const u64 last = ntiles ? tile_state[ntiles - 1] : 0;
-  __syncthreads();
+  exp_sync<TINY>();
   for (u32 i = tid; i < ntiles; i += EXP_THREADS) tile_state[i] = 0;
   if (tid == 0) {
     u32 ovf = ctl->overflow;
@@ -317,6 +395,11 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
     ctl->tile_ticket = 0;
     ctl->blocks_done = 0;
   }
+}
+
+__global__ void __launch_bounds__(EXP_THREADS, EXP_MIN_BLOCKS)
+k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+  expand_level<false>(Dp, Ap, ctl);
 }
 
 /* fp64 FMA peak of this device, measured (denominator for K1's fp64 figure): 8 independent chains/thread */

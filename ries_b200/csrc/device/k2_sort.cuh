@@ -99,7 +99,12 @@ k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
    order). */
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)
+#ifndef RS_ITEMS
 #define RS_ITEMS 16
+#endif
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 2
+#endif
 #define RS_CHUNK (RS_THREADS * RS_ITEMS)
 #define RS_FLAG_AGG 1ull
 #define RS_FLAG_INC 2ull
@@ -112,7 +117,7 @@ k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
      exchange keys go to shared memory in their chunk-local sorted position, and are written out from
               there so that neighbouring threads write neighbouring addresses of the same bin
    The order inside a bin is (chunk, warp, round, lane) = input order, so the sort is stable. */
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass) {
   extern __shared__ __align__(16) unsigned char s_rs_dyn[];
   u64* s_keys = (u64*)s_rs_dyn;

@@ -3,11 +3,10 @@
 #pragma once
 
 /* K4 */
-__global__ void k_refine(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+__device__ __forceinline__ void refine_body(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
   __shared__ RiesParams P;
-  if (C->overflow) return;
-  u32 n = C->n_events;
-  if (n == 0) return;
+  u32 n = C->overflow ? 0 : C->n_events;
+  if (n == 0) return; /* uniform over the block */
   if (n > A->cap_events) n = A->cap_events;
   {
     const u32* src = (const u32*)Dp->P;
@@ -22,4 +21,8 @@ __global__ void k_refine(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C)
     refine_event(P, ev);
     events[i] = ev;
   }
+}
+
+__global__ void k_refine(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+  refine_body(Dp, A, C);
 }

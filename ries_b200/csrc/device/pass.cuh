@@ -4,7 +4,7 @@
 
 /* ---------------------------------------------------------------- pass begin / end ------ */
 
-__global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+__device__ __forceinline__ void pass_begin_body(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   const u32 nforms = (u32)A->nforms;
   const u32 world = (u32)A->shard_world, rank = (u32)A->shard_rank;
   const u32 nroots = (nforms > rank) ? (nforms - rank + world - 1) / world : 0; /* forms dealt round-robin */
@@ -25,13 +25,18 @@ __global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, Ta
     C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
     C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
     C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0;
+    C->tiny_k1_ns = 0; C->tiny_post_ns = 0;
     u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
     if (e == 0) e = 16;
     T->epoch = e;
   }
 }
 
-__global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+__global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+  pass_begin_body(D, A, C, T);
+}
+
+__device__ __forceinline__ void pass_end_body(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   if (threadIdx.x == 0 && !C->overflow && C->n_uniq) {
     T->cur ^= 1u;
     T->nt += C->n_uniq;
@@ -43,4 +48,8 @@ __global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, Tabl
   const u32* src = (const u32*)D->events;
   u32* dst = (u32*)((PassOut*)C)->head;
   for (u32 i = threadIdx.x; i < ne * (sizeof(MatchEvent) / 4); i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+  pass_end_body(D, A, C, T);
 }

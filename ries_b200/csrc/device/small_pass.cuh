@@ -77,8 +77,35 @@ __device__ __forceinline__ void small_sort_pass(u64* s_keys, u32* s_pays, u32* s
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(SP_THREADS, 1)
-k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+/* m <= SP_THREADS keys: one key per thread, its final position = the number of keys that sort before it
+   (smaller, or equal and earlier: stable).  m broadcast reads of shared memory per thread and two barriers
+   instead of eight digit passes of five barriers each. */
+__device__ __forceinline__ void small_rank_sort(u64* s_keys, u32* s_pays, u32 m) {
+  const u32 tid = threadIdx.x;
+  u64 k = 0;
+  u32 p = 0, rank = 0;
+  if (tid < m) {
+    k = s_keys[tid];
+    p = s_pays[tid];
+    u32 j = 0;
+    for (; j + 4 <= m; j += 4) {
+      const u64 o0 = s_keys[j], o1 = s_keys[j + 1], o2 = s_keys[j + 2], o3 = s_keys[j + 3];
+      rank += (u32)((o0 < k) || (o0 == k && j < tid));
+      rank += (u32)((o1 < k) || (o1 == k && j + 1 < tid));
+      rank += (u32)((o2 < k) || (o2 == k && j + 2 < tid));
+      rank += (u32)((o3 < k) || (o3 == k && j + 3 < tid));
+    }
+    for (; j < m; j++) {
+      const u64 o = s_keys[j];
+      rank += (u32)((o < k) || (o == k && j < tid));
+    }
+  }
+  __syncthreads();
+  if (tid < m) { s_keys[rank] = k; s_pays[rank] = p; }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
   extern __shared__ __align__(16) unsigned char s_sp_dyn[];
   u64* s_keys = (u64*)s_sp_dyn;
   u32* s_pays = (u32*)(s_keys + SP_CAP);
@@ -99,12 +126,18 @@ k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState*
   const DevPtrs D = *Dp;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   /* insertion order: stable sort of the done[] indices by form */
-  const Row* __restrict__ done = A->gathered ? D.gdone : D.done;
-  const uint16_t* __restrict__ done_form = A->gathered ? D.gdone_form : D.done_form;
+  /* (no __restrict__: in k_tiny_front these were written earlier in the same kernel) */
+  const Row* done = A->gathered ? D.gdone : D.done;
+  const uint16_t* done_form = A->gathered ? D.gdone_form : D.done_form;
   for (u32 i = tid; i < n; i += SP_THREADS) { s_keys[i] = done_form[i]; s_pays[i] = i; }
   __syncthreads();
-  small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 0);
-  if (A->nforms > 256) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 8);
+  const bool by_rank = n <= SP_THREADS;
+  if (by_rank) {
+    small_rank_sort(s_keys, s_pays, n);
+  } else {
+    small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 0);
+    if (A->nforms > 256) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, 8);
+  }
   for (u32 j = tid; j < n; j += SP_THREADS) {
     const Row r = done[s_pays[j]];
     D.surv[j] = r;
@@ -113,7 +146,11 @@ k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState*
   }
   __syncthreads();
   /* stable sort by value */
-  for (int pass = 0; pass < 8; pass++) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, pass * 8);
+  if (by_rank) {
+    small_rank_sort(s_keys, s_pays, n);
+  } else {
+    for (int pass = 0; pass < 8; pass++) small_sort_pass(s_keys, s_pays, s_whist, s_binex, s_wtot, n, pass * 8);
+  }
   /* classify: new distinct values, EXACT events */
   const u32 cur = T->cur, nt = T->nt;
   const double* __restrict__ tval = D.tval[cur];
@@ -236,4 +273,9 @@ k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState*
       push_event(D.events, A->cap_events, C, sidx, side == 0 ? EV_PREV : EV_NEXT, L, R);
     }
   }
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+  small_post_body(Dp, A, C, T);
 }

@@ -44,6 +44,9 @@ struct PassCtl {
   u64 dead;               /* dead-ends of the pass */
   u32 aux_ticket;         /* k_local_filter / k_compact_kept (sharded passes) */
   u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
+  /* k_tiny_front (one kernel for K1 + regroup/sort/classify/match): device time of its two halves, so that
+     the host can still book them under their stages */
+  u32 tiny_k1_ns, tiny_post_ns;
 };
 
 #define HEAD_EVENTS 16 /* candidates copied back together with the counters (one copy, one sync per pass) */

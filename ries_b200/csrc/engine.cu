@@ -65,6 +65,7 @@ typedef unsigned int u32;
 #include "device/shard.cuh"
 #include "device/merge_old.cuh"
 #include "device/k4_refine.cuh"
+#include "device/tiny_pass.cuh"
 
 /* ---------------------------------------------------------------- host-side engine ------- */
 
@@ -129,6 +130,12 @@ class DeviceEngine : public Engine {
     use_graphs_ = getenv("RIES_NO_GRAPHS") == 0;
     use_small_post_ = getenv("RIES_NO_SMALL_POST") == 0; /* test hook: every pass through the general kernels */
     force_small_post_ = getenv("RIES_FORCE_SMALL_POST") != 0;
+    /* tiny passes (tiny_pass.cuh): RIES_NO_TINY switches them off, RIES_TINY_NODES / RIES_TINY_FRONTIER move the
+       prediction threshold and the frontier width at which the kernel gives up (test hooks) */
+    use_tiny_ = getenv("RIES_NO_TINY") == 0;
+    if (const char* e = getenv("RIES_TINY_NODES")) tiny_nodes_ = (u32)strtoul(e, 0, 10);
+    if (const char* e = getenv("RIES_TINY_FRONTIER")) tiny_frontier_ = (u32)strtoul(e, 0, 10);
+    CUDA_CHECK(cudaFuncSetAttribute(k_tiny_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TINY_DYN_SMEM));
     pass_log_ = getenv("RIES_PASS_LOG") != 0; /* one line per pass on stderr: sizes and device time per stage */
     CUDA_CHECK(cudaFuncSetAttribute(k_small_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_DYN_SMEM));
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
@@ -211,6 +218,7 @@ class DeviceEngine : public Engine {
     for (int i = 0; i < 4; i++) { stage_ms[i] = 0; stage_launches[i] = 0; }
     sort_keys = merge_rows = expand_nodes = 0;
     sharded_passes = gather_bytes = 0;
+    tiny_passes = 0;
     gather_ms = 0;
   }
 
@@ -243,7 +251,7 @@ class DeviceEngine : public Engine {
 
     bool no_small_post = !use_small_post_;
     unsigned long long gen_k1 = 0; /* sharded passes: complete expressions of all ranks' K1, before the pre-dedupe */
-    bool was_sharded = false;
+    bool was_sharded = false, was_tiny = false;
     {
       /* sizes grow ~1.3-1.6x per complexity step: keep twice the previous same-side pass in hand, so that
          the overflow-and-rerun path stays the exception (it costs a whole pass) */
@@ -274,9 +282,20 @@ class DeviceEngine : public Engine {
       h_args_->gathered = 0; /* a sharded pass switches to the gathered arrays after the exchange */
       h_args_->pad2 = 0;
       if (shard && small == 2) small = 1; /* the single-block kernel has no local/global split */
+      /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh) */
+      const bool tiny = use_tiny_ && small == 2 && !force_small_post_ && !shard &&
+                        prev_nodes_[using_x ? 1 : 0] <= tiny_nodes_;
       CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                  cudaMemcpyHostToDevice, st_));
-      if (!shard) {
+      was_tiny = tiny;
+      if (tiny) {
+        launch_tiny();
+        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        CUDA_CHECK(cudaGetLastError());
+        d2h_bytes += sizeof(PassOut);
+        collect_tiny_times();
+      } else if (!shard) {
         launch_stages(0, 3, max_len, small);
         CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -321,10 +340,20 @@ class DeviceEngine : public Engine {
     const u32 n = h_ctl_->done_count, nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
     if (pass_log_) {
       float ms[4] = {0, 0, 0, 0};
-      for (int i = 0; i < 4; i++) (void)cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]);
+      if (was_tiny) {
+        float front = 0;
+        (void)cudaEventElapsedTime(&front, ev_[0], ev_[2]);
+        const double a = h_ctl_->tiny_k1_ns, b = h_ctl_->tiny_post_ns;
+        ms[0] = (float)(front * ((a + b > 0) ? a / (a + b) : 1.0));
+        ms[1] = front - ms[0];
+        (void)cudaEventElapsedTime(&ms[2], ev_[2], ev_[3]);
+        (void)cudaEventElapsedTime(&ms[3], ev_[3], ev_[4]);
+      } else {
+        for (int i = 0; i < 4; i++) (void)cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]);
+      }
       (void)cudaGetLastError();
       fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
-              using_x ? "LHS" : "RHS", cplx, nforms, max_len, h_ctl_->node_count, n, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
+              using_x ? (was_tiny ? "lhs" : "LHS") : (was_tiny ? "rhs" : "RHS"), cplx, nforms, max_len, h_ctl_->node_count, n, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
     }
     const unsigned long long gen = was_sharded ? gen_k1 : (unsigned long long)n;
     prev_nodes_[using_x ? 1 : 0] = h_ctl_->node_count;
@@ -369,6 +398,7 @@ class DeviceEngine : public Engine {
   unsigned long long sort_keys = 0;      /* survivors that went through the radix sort */
   unsigned long long merge_rows = 0;     /* rows written by the merges (old + new) */
   unsigned long long expand_nodes = 0;   /* live prefixes expanded (= exec'd prefixes) */
+  unsigned long long tiny_passes = 0;    /* passes that went through the three-launch tiny path */
   unsigned long long sharded_passes = 0; /* passes whose K1 ran sharded over the ranks */
   unsigned long long gather_bytes = 0;   /* bytes this rank received/kept in the all-gathers */
   double gather_ms = 0;                  /* device time of the all-gathers (CUDA events) */
@@ -409,7 +439,7 @@ class DeviceEngine : public Engine {
        exit at once costs more than the work itself.  A wrong prediction is slow, never wrong. */
     const u32 g_exp = small ? 24u : expand_grid_;
     const u32 g_wide = small ? 12u : wide_grid_;
-    const u32 g_sort = small ? 12u : (u32)num_sms_ * 2;
+    const u32 g_sort = small ? 12u : (u32)num_sms_ * RS_MIN_BLOCKS;
     switch (stage) {
       case 0:
         k_pass_begin<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
@@ -482,6 +512,35 @@ class DeviceEngine : public Engine {
       kernel_launches += k;
       stage_launches[stage] += k;
     }
+  }
+
+  /* A pass predicted tiny: three direct launches (tiny_pass.cuh).  ev_[0] .. ev_[2] brackets the fused front
+     kernel, whose own two halves are booked from the device timestamps it leaves in the control block. */
+  void launch_tiny() {
+    bump_epoch();
+    CUDA_CHECK(cudaEventRecord(ev_[0], st_));
+    k_tiny_front<<<1, TINY_THREADS, TINY_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, tiny_frontier_);
+    CUDA_CHECK(cudaEventRecord(ev_[2], st_));
+    k_merge_old<<<48u, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+    CUDA_CHECK(cudaEventRecord(ev_[3], st_));
+    k_refine_end<<<1, 128, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+    CUDA_CHECK(cudaEventRecord(ev_[4], st_));
+    kernel_launches += 3;
+    stage_launches[0] += 1; stage_launches[2] += 1; stage_launches[3] += 1;
+    tiny_passes++;
+  }
+
+  void collect_tiny_times() {
+    float front = 0, ms = 0;
+    if (cudaEventElapsedTime(&front, ev_[0], ev_[2]) == cudaSuccess) {
+      const double a = h_ctl_->tiny_k1_ns, b = h_ctl_->tiny_post_ns;
+      const double fa = (a + b > 0) ? a / (a + b) : 1.0;
+      stage_ms[0] += front * fa;
+      stage_ms[1] += front * (1.0 - fa);
+    }
+    if (cudaEventElapsedTime(&ms, ev_[2], ev_[3]) == cudaSuccess) stage_ms[2] += ms;
+    if (cudaEventElapsedTime(&ms, ev_[3], ev_[4]) == cudaSuccess) stage_ms[3] += ms;
+    (void)cudaGetLastError();
   }
 
   void collect_stage_times(int first, int last) {
@@ -641,6 +700,8 @@ class DeviceEngine : public Engine {
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
+  bool use_tiny_ = true;
+  u32 tiny_nodes_ = 1200, tiny_frontier_ = 2048;
   std::map<int, cudaGraphExec_t> graphs_;
   RiesParams* d_P_ = 0;
   TestTables* d_tt_ = 0;

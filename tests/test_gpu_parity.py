@@ -110,13 +110,17 @@ def test_gpu_node_arena_regrow(product_lib):
                                        {"RIES_NO_GRAPHS": "1"},
                                        {"RIES_FAKE_SHARD": "3", "RIES_SHARD_MIN": "0"},
                                        {"RIES_FAKE_SHARD": "2", "RIES_SHARD_MIN": "2000", "RIES_ARENA_CAP": "4096"},
-                                       {"RIES_FORMS_SLICE": "7"}],
+                                       {"RIES_FORMS_SLICE": "7"},
+                                       {"RIES_NO_TINY": "1"},
+                                       {"RIES_TINY_NODES": "100000", "RIES_TINY_FRONTIER": "48"},
+                                       {"RIES_TINY_NODES": "100000", "RIES_TINY_FRONTIER": "100000"}],
                          ids=["general-kernels-only", "mispredicted-small-pass", "no-graphs",
                               "every-pass-sharded-3-virtual-ranks", "large-passes-sharded-2-virtual-ranks-regrow",
-                              "passes-fed-in-slices-of-7-forms"])
+                              "passes-fed-in-slices-of-7-forms", "no-tiny-passes", "mispredicted-tiny-pass",
+                              "every-small-pass-tiny"])
 def test_gpu_pass_variants_agree(product_lib, env_extra):
-    """Small passes run through a fused single-block kernel, the rest through the general kernels, a wrong
-    size prediction is rerun, and K1 can be sharded over (virtual) ranks with the complete expressions
+    """Tiny passes run as three launches (one block enumerates, sorts and matches), small passes through a
+    fused single-block post kernel, the rest through the general kernels, a wrong size prediction is rerun, and K1 can be sharded over (virtual) ranks with the complete expressions
     gathered rank-major: every route must print the same bytes."""
     import subprocess
     env = dict(os.environ, HOME="/nonexistent", **env_extra)
