@@ -77,31 +77,28 @@ __device__ __forceinline__ void small_sort_pass(u64* s_keys, u32* s_pays, u32* s
   __syncthreads();
 }
 
-/* m <= SP_THREADS keys: one key per thread, its final position = the number of keys that sort before it
-   (smaller, or equal and earlier: stable).  m broadcast reads of shared memory per thread and two barriers
-   instead of eight digit passes of five barriers each. */
+/* m <= SP_THREADS keys: the final position of a key = the number of keys that sort before it (smaller, or
+   equal and earlier: stable).  `tpk` threads share a key (a power of two, as many as the block has to
+   spare, all in one warp) and each counts over every tpk-th key; the partial counts meet by shuffle.  m / tpk
+   broadcast reads of shared memory per thread and two barriers instead of eight digit passes of five. */
 __device__ __forceinline__ void small_rank_sort(u64* s_keys, u32* s_pays, u32 m) {
   const u32 tid = threadIdx.x;
+  u32 tpk = 1;
+  while (tpk < 32 && m * tpk * 2 <= SP_THREADS) tpk <<= 1;
+  const u32 ki = tid / tpk, sub = tid % tpk;
   u64 k = 0;
   u32 p = 0, rank = 0;
-  if (tid < m) {
-    k = s_keys[tid];
-    p = s_pays[tid];
-    u32 j = 0;
-    for (; j + 4 <= m; j += 4) {
-      const u64 o0 = s_keys[j], o1 = s_keys[j + 1], o2 = s_keys[j + 2], o3 = s_keys[j + 3];
-      rank += (u32)((o0 < k) || (o0 == k && j < tid));
-      rank += (u32)((o1 < k) || (o1 == k && j + 1 < tid));
-      rank += (u32)((o2 < k) || (o2 == k && j + 2 < tid));
-      rank += (u32)((o3 < k) || (o3 == k && j + 3 < tid));
-    }
-    for (; j < m; j++) {
+  if (ki < m) {
+    k = s_keys[ki];
+    p = s_pays[ki];
+    for (u32 j = sub; j < m; j += tpk) {
       const u64 o = s_keys[j];
-      rank += (u32)((o < k) || (o == k && j < tid));
+      rank += (u32)((o < k) || (o == k && j < ki));
     }
   }
+  for (u32 o = 1; o < tpk; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
   __syncthreads();
-  if (tid < m) { s_keys[rank] = k; s_pays[rank] = p; }
+  if (ki < m && sub == 0) { s_keys[rank] = k; s_pays[rank] = p; }
   __syncthreads();
 }
 
