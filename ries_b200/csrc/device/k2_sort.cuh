@@ -8,6 +8,7 @@
 __device__ __forceinline__ bool pass_ok(const PassCtl* C) { return (C->overflow & (OVF_NODES | OVF_DONE)) == 0; }
 
 __global__ void k_form_bounds(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+  stage_stamp(C, 1);
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
   const uint16_t* done_form = A->gathered ? Dp->gdone_form : Dp->done_form;

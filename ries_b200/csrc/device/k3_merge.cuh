@@ -68,6 +68,7 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   __shared__ double s_win[CC_WIN + 1];
   __shared__ u32 s_cnt[CC_ITEMS * (CC_THREADS / 32)];
   __shared__ u32 s_chunk, s_base, s_lo, s_hi;
+  stage_stamp(C, 2);
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
   const u32 nchunks = (n + CC_CHUNK - 1) / CC_CHUNK;

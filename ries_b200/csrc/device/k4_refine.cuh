@@ -24,5 +24,6 @@ __device__ __forceinline__ void refine_body(const DevPtrs* Dp, const PassArgs* A
 }
 
 __global__ void k_refine(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+  stage_stamp(C, 3);
   refine_body(Dp, A, C);
 }

@@ -25,7 +25,7 @@ __device__ __forceinline__ void pass_begin_body(const DevPtrs* D, const PassArgs
     C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
     C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
     C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0;
-    C->tiny_k1_ns = 0; C->tiny_post_ns = 0;
+    C->stamp[1] = C->stamp[2] = C->stamp[3] = C->stamp[4] = 0;
     u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
     if (e == 0) e = 16;
     T->epoch = e;
@@ -33,6 +33,7 @@ __device__ __forceinline__ void pass_begin_body(const DevPtrs* D, const PassArgs
 }
 
 __global__ void k_pass_begin(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
+  stage_stamp(C, 0);
   pass_begin_body(D, A, C, T);
 }
 
@@ -52,4 +53,6 @@ __device__ __forceinline__ void pass_end_body(const DevPtrs* D, const PassArgs* 
 
 __global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   pass_end_body(D, A, C, T);
+  __syncthreads();
+  stage_stamp(C, 4);
 }

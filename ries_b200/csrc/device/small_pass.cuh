@@ -274,5 +274,8 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
 
 __global__ void __launch_bounds__(SP_THREADS, 1)
 k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+  stage_stamp(C, 1);
   small_post_body(Dp, A, C, T);
+  __syncthreads();
+  stage_stamp(C, 2); /* k_merge_old is all there is to stage 2 after this kernel */
 }

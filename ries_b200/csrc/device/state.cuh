@@ -44,10 +44,21 @@ struct PassCtl {
   u64 dead;               /* dead-ends of the pass */
   u32 aux_ticket;         /* k_local_filter / k_compact_kept (sharded passes) */
   u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
-  /* k_tiny_front (one kernel for K1 + regroup/sort/classify/match): device time of its two halves, so that
-     the host can still book them under their stages */
-  u32 tiny_k1_ns, tiny_post_ns;
+  /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] regroup +
+     sort, [2] classify/match/merge, [3] refine, [4] end.  Written by thread 0 of block 0 of the stage's first
+     kernel (the kernels of a pass run back to back on one stream), read by the host from the copied-back
+     block: per-stage device time without a CUDA event per stage on the host's critical path. */
+  u64 stamp[5];
 };
+
+__device__ __forceinline__ u64 dev_now_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stage_stamp(const PassCtl* C, int i) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) ((PassCtl*)C)->stamp[i] = dev_now_ns();
+}
 
 #define HEAD_EVENTS 16 /* candidates copied back together with the counters (one copy, one sync per pass) */
 struct PassOut {

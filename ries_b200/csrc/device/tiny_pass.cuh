@@ -17,18 +17,12 @@
 #define TINY_THREADS SP_THREADS
 #define TINY_DYN_SMEM ((EXP_DYN_SMEM > SP_DYN_SMEM) ? EXP_DYN_SMEM : SP_DYN_SMEM)
 
-__device__ __forceinline__ u64 tiny_now_ns() {
-  u64 t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 __global__ void __launch_bounds__(TINY_THREADS, 1)
 k_tiny_front(const DevPtrs* Dp, const PassArgs* Ap, PassCtl* ctl, TableState* T, u32 max_frontier) {
+  stage_stamp(ctl, 0);
   pass_begin_body(Dp, Ap, ctl, T);
   __threadfence();
   __syncthreads();
-  const u64 t0 = tiny_now_ns();
   if (threadIdx.x < EXP_THREADS) {
     /* the frontier bounds of the next position come back through the control block, written by thread 0
        before expand_level's closing barrier */
@@ -45,18 +39,20 @@ k_tiny_front(const DevPtrs* Dp, const PassArgs* Ap, PassCtl* ctl, TableState* T,
   }
   __threadfence();
   __syncthreads();
-  const u64 t1 = tiny_now_ns();
-  if (threadIdx.x == 0) ctl->tiny_k1_ns = (u32)(t1 - t0);
+  stage_stamp(ctl, 1);
   if (ctl->overflow & OVF_SMALL) return; /* uniform */
   small_post_body(Dp, Ap, ctl, T);
   __syncthreads();
-  if (threadIdx.x == 0) ctl->tiny_post_ns = (u32)(tiny_now_ns() - t1);
+  stage_stamp(ctl, 2);
 }
 
 __global__ void __launch_bounds__(128)
 k_refine_end(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, TableState* T) {
+  stage_stamp(C, 3);
   refine_body(Dp, A, C);
   __threadfence();
   __syncthreads();
   pass_end_body(Dp, A, C, T);
+  __syncthreads();
+  stage_stamp(C, 4);
 }

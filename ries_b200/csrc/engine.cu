@@ -30,6 +30,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <map>
@@ -136,6 +137,7 @@ class DeviceEngine : public Engine {
     if (const char* e = getenv("RIES_TINY_NODES")) tiny_nodes_ = (u32)strtoul(e, 0, 10);
     if (const char* e = getenv("RIES_TINY_FRONTIER")) tiny_frontier_ = (u32)strtoul(e, 0, 10);
     CUDA_CHECK(cudaFuncSetAttribute(k_tiny_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TINY_DYN_SMEM));
+    host_prof_ = getenv("RIES_HOST_PROF") != 0; /* host time per pass phase, printed at the next begin()/exit */
     pass_log_ = getenv("RIES_PASS_LOG") != 0; /* one line per pass on stderr: sizes and device time per stage */
     CUDA_CHECK(cudaFuncSetAttribute(k_small_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_DYN_SMEM));
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
@@ -195,6 +197,11 @@ class DeviceEngine : public Engine {
   const char* name() const override { return "sm_100a"; }
 
   void begin(const RiesParams& P) override {
+    if (host_prof_ && hp_[5] > 0) {
+      fprintf(stderr, "host per pass (us): prepare %.1f enqueue %.1f wait %.1f collect %.1f events %.1f over %.0f passes\n",
+              hp_[0] / hp_[5], hp_[1] / hp_[5], hp_[2] / hp_[5], hp_[3] / hp_[5], hp_[4] / hp_[5], hp_[5]);
+      for (double& v : hp_) v = 0;
+    }
     if (!test_tables_cover(P)) {
       fprintf(stderr, "ries_b200: a symbol weight is outside the test tables' range\n");
       abort();
@@ -237,6 +244,7 @@ class DeviceEngine : public Engine {
     last_nu_ = 0;
     const u32 nforms = (u32)forms.size();
     if (nforms == 0) return;
+    double hp_t0 = host_prof_ ? now_us() : 0, hp_t1 = 0, hp_t2 = 0, hp_t3 = 0;
     if (nforms > PASSIN_MAX_FORMS - 1) {
       fprintf(stderr, "ries_b200: %u forms in one pass exceeds the 16-bit form index\n", nforms);
       abort();
@@ -289,19 +297,25 @@ class DeviceEngine : public Engine {
                                  cudaMemcpyHostToDevice, st_));
       was_tiny = tiny;
       if (tiny) {
+        if (host_prof_) hp_t1 = now_us();
         launch_tiny();
         CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
+        if (host_prof_) hp_t2 = now_us();
         CUDA_CHECK(cudaStreamSynchronize(st_));
+        if (host_prof_) hp_t3 = now_us();
         CUDA_CHECK(cudaGetLastError());
         d2h_bytes += sizeof(PassOut);
-        collect_tiny_times();
+        collect_stamp_times();
       } else if (!shard) {
+        if (host_prof_) hp_t1 = now_us();
         launch_stages(0, 3, max_len, small);
         CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
+        if (host_prof_) hp_t2 = now_us();
         CUDA_CHECK(cudaStreamSynchronize(st_));
+        if (host_prof_) hp_t3 = now_us();
         CUDA_CHECK(cudaGetLastError());
         d2h_bytes += sizeof(PassOut);
-        collect_stage_times(0, 3);
+        collect_stamp_times();
       } else {
         size_t want_nodes = nodes_.cap, want_done = done_.cap;
         const u32 fovf = sharded_front(max_len, small, &want_nodes, &want_done, &gen_k1);
@@ -312,7 +326,7 @@ class DeviceEngine : public Engine {
         }
         sharded_passes++;
         was_sharded = true;
-        launch_stages(1, 3, max_len, small);
+        launch_stages(1, 3, max_len, small, true);
         CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
         CUDA_CHECK(cudaGetLastError());
@@ -338,20 +352,9 @@ class DeviceEngine : public Engine {
       if (ovf & OVF_SMALL) no_small_post = true;
     }
     const u32 n = h_ctl_->done_count, nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
+    const double hp_t4 = host_prof_ ? now_us() : 0;
     if (pass_log_) {
-      float ms[4] = {0, 0, 0, 0};
-      if (was_tiny) {
-        float front = 0;
-        (void)cudaEventElapsedTime(&front, ev_[0], ev_[2]);
-        const double a = h_ctl_->tiny_k1_ns, b = h_ctl_->tiny_post_ns;
-        ms[0] = (float)(front * ((a + b > 0) ? a / (a + b) : 1.0));
-        ms[1] = front - ms[0];
-        (void)cudaEventElapsedTime(&ms[2], ev_[2], ev_[3]);
-        (void)cudaEventElapsedTime(&ms[3], ev_[3], ev_[4]);
-      } else {
-        for (int i = 0; i < 4; i++) (void)cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]);
-      }
-      (void)cudaGetLastError();
+      const float* ms = last_ms_;
       fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
               using_x ? (was_tiny ? "lhs" : "LHS") : (was_tiny ? "rhs" : "RHS"), cplx, nforms, max_len, h_ctl_->node_count, n, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
     }
@@ -386,6 +389,10 @@ class DeviceEngine : public Engine {
       std::sort(out.events.begin(), out.events.end(), [](const MatchEvent& a, const MatchEvent& b) {
         return a.seq != b.seq ? a.seq < b.seq : a.kind < b.kind;
       });
+    }
+    if (host_prof_ && hp_t1 > 0) {
+      hp_[0] += hp_t1 - hp_t0; hp_[1] += hp_t2 - hp_t1; hp_[2] += hp_t3 - hp_t2; hp_[3] += hp_t4 - hp_t3;
+      hp_[4] += now_us() - hp_t4; hp_[5] += 1;
     }
   }
 
@@ -483,10 +490,12 @@ class DeviceEngine : public Engine {
     }
   }
 
-  /* Stages [first, last] of a pass on the stream; ev_[k] is recorded before stage k (and after the last). */
-  void launch_stages(int first, int last, int max_len, int small) {
+  /* Stages [first, last] of a pass on the stream.  Per-stage device time comes from the device clock stamps
+     the kernels leave in the control block (collect_stamp_times); only sharded passes, whose stages are
+     interleaved with the exchange, bracket them with CUDA events (ev_[k] before stage k and after the last). */
+  void launch_stages(int first, int last, int max_len, int small, bool events = false) {
     if (first == 0) bump_epoch();
-    CUDA_CHECK(cudaEventRecord(ev_[first], st_));
+    if (events) CUDA_CHECK(cudaEventRecord(ev_[first], st_));
     for (int stage = first; stage <= last; stage++) {
       if (!use_graphs_) {
         enqueue_stage(stage, max_len, small);
@@ -505,7 +514,7 @@ class DeviceEngine : public Engine {
         }
         CUDA_CHECK(cudaGraphLaunch(it->second, st_));
       }
-      CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
+      if (events) CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
       const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1
                                  : (stage == 1) ? ((small == 2) ? 1 : 11)
                                  : (stage == 2) ? ((small == 2) ? 1 : 3) : 2;
@@ -514,39 +523,34 @@ class DeviceEngine : public Engine {
     }
   }
 
-  /* A pass predicted tiny: three direct launches (tiny_pass.cuh).  ev_[0] .. ev_[2] brackets the fused front
-     kernel, whose own two halves are booked from the device timestamps it leaves in the control block. */
+  /* A pass predicted tiny: three direct launches (tiny_pass.cuh). */
   void launch_tiny() {
     bump_epoch();
-    CUDA_CHECK(cudaEventRecord(ev_[0], st_));
     k_tiny_front<<<1, TINY_THREADS, TINY_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, tiny_frontier_);
-    CUDA_CHECK(cudaEventRecord(ev_[2], st_));
     k_merge_old<<<48u, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
-    CUDA_CHECK(cudaEventRecord(ev_[3], st_));
     k_refine_end<<<1, 128, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-    CUDA_CHECK(cudaEventRecord(ev_[4], st_));
     kernel_launches += 3;
     stage_launches[0] += 1; stage_launches[2] += 1; stage_launches[3] += 1;
     tiny_passes++;
   }
 
-  void collect_tiny_times() {
-    float front = 0, ms = 0;
-    if (cudaEventElapsedTime(&front, ev_[0], ev_[2]) == cudaSuccess) {
-      const double a = h_ctl_->tiny_k1_ns, b = h_ctl_->tiny_post_ns;
-      const double fa = (a + b > 0) ? a / (a + b) : 1.0;
-      stage_ms[0] += front * fa;
-      stage_ms[1] += front * (1.0 - fa);
+  /* device time per stage of the pass just synchronised, from the stamps in the copied-back control block */
+  void collect_stamp_times() {
+    const u64* t = h_ctl_->stamp;
+    for (int i = 0; i < 4; i++) {
+      last_ms_[i] = 0;
+      if (!t[i]) continue;
+      int j = i + 1;
+      while (j < 4 && !t[j]) j++; /* a stage that never started (overflow) leaves no stamp */
+      if (t[j] >= t[i]) last_ms_[i] = (float)((double)(t[j] - t[i]) * 1e-6);
+      stage_ms[i] += last_ms_[i];
     }
-    if (cudaEventElapsedTime(&ms, ev_[2], ev_[3]) == cudaSuccess) stage_ms[2] += ms;
-    if (cudaEventElapsedTime(&ms, ev_[3], ev_[4]) == cudaSuccess) stage_ms[3] += ms;
-    (void)cudaGetLastError();
   }
 
   void collect_stage_times(int first, int last) {
     for (int i = first; i <= last; i++) {
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]) == cudaSuccess) stage_ms[i] += ms;
+      if (cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]) == cudaSuccess) { stage_ms[i] += ms; last_ms_[i] = ms; }
     }
     (void)cudaGetLastError();
   }
@@ -569,7 +573,7 @@ class DeviceEngine : public Engine {
     const u32 g_wide = small ? 12u : wide_grid_;
     /* K1 -> regroup + sort of this rank's own expressions -> drop what cannot matter -> compact */
     auto local_front = [&]() {
-      launch_stages(0, 1, max_len, small);
+      launch_stages(0, 1, max_len, small, true);
       k_local_filter<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
       k_compact_kept<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
       bump_epoch();
@@ -700,7 +704,13 @@ class DeviceEngine : public Engine {
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
-  bool use_tiny_ = true;
+  bool use_tiny_ = true, host_prof_ = false;
+  double hp_[6] = {0, 0, 0, 0, 0, 0}; /* prepare, enqueue, wait, collect, events, passes */
+  static double now_us() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+  }
   u32 tiny_nodes_ = 1200, tiny_frontier_ = 2048;
   std::map<int, cudaGraphExec_t> graphs_;
   RiesParams* d_P_ = 0;
@@ -722,6 +732,7 @@ class DeviceEngine : public Engine {
   SortCtl* d_sortctl_ = 0;
   u64* d_opcnt_ = 0;
   cudaEvent_t ev_[5];
+  float last_ms_[4] = {0, 0, 0, 0}; /* per-stage device time of the last pass (pass log) */
   cudaEvent_t ev_g_[2];
   bool gather_pending_ = false;
   FormDesc* h_forms_ = 0;
