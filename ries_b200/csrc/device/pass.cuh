@@ -51,8 +51,30 @@ __device__ __forceinline__ void pass_end_body(const DevPtrs* D, const PassArgs* 
   for (u32 i = threadIdx.x; i < ne * (sizeof(MatchEvent) / 4); i += blockDim.x) dst[i] = src[i];
 }
 
+/* The very end of a pass (single block, after pass_end_body and the last stamp): the control block and the head
+   candidates go straight into the host's mapped buffer, then the pass number -- the host polls for it instead of
+   paying for a copy operation and a stream synchronisation per pass. */
+__device__ __forceinline__ void post_to_host(const DevPtrs* D, const PassArgs* A, PassCtl* C) {
+  __syncthreads();
+  PassOut* h = D->host_out;
+  u32 ne = C->n_events;
+  if (ne > A->cap_events) ne = A->cap_events;
+  if (ne > HEAD_EVENTS) ne = HEAD_EVENTS;
+  const u32 words = (u32)(offsetof(PassOut, head) / 4) + ne * (u32)(sizeof(MatchEvent) / 4);
+  const volatile u32* src = (const volatile u32*)C;
+  volatile u32* dst = (volatile u32*)h;
+  for (u32 i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *(volatile u32*)&h->seq = A->seq;
+    __threadfence_system();
+  }
+}
+
 __global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   pass_end_body(D, A, C, T);
   __syncthreads();
   stage_stamp(C, 4);
+  post_to_host(D, A, C);
 }

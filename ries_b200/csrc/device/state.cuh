@@ -24,7 +24,8 @@ struct __attribute__((aligned(8))) Staged { /* a child between phase 3 and phase
 struct PassArgs {
   int using_x, cplx, skip_exact, nforms;
   double best_match0;
-  u32 cap_nodes, cap_done, cap_events, pad;
+  u32 cap_nodes, cap_done, cap_events;
+  u32 seq; /* number of this pass launch: the last kernel posts it to the host together with the results */
   /* one search over several GPUs: this rank enumerates the forms f with f % shard_world == shard_rank, and
      the regroup kernels read the all-gathered complete expressions instead of this rank's own */
   int shard_rank, shard_world, gathered, pad2;
@@ -64,6 +65,8 @@ __device__ __forceinline__ void stage_stamp(const PassCtl* C, int i) {
 struct PassOut {
   PassCtl ctl;
   MatchEvent head[HEAD_EVENTS];
+  u32 seq; /* host copy only: PassArgs::seq of the pass whose results are complete in this block */
+  u32 pad[3];
 };
 
 /* What the host sends per pass, in one copy: the scalars, then the forms. */
@@ -110,4 +113,5 @@ struct DevPtrs {
   u64* cc_state;  /* classify look-back state, one word per chunk */
   SortCtl* sortctl;
   u64* opcnt;
+  PassOut* host_out; /* mapped pinned host memory: the last kernel of a pass writes its results there itself */
 };

@@ -55,4 +55,5 @@ k_refine_end(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, TableState* T) {
   pass_end_body(Dp, A, C, T);
   __syncthreads();
   stage_stamp(C, 4);
+  post_to_host(Dp, A, C);
 }

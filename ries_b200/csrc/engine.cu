@@ -27,6 +27,7 @@
 //   surv[]    32 B rows, the pass's complete expressions in insertion (DFS) order
 // No tensor cores: nothing here is a dense contraction.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -153,7 +154,10 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMalloc(&d_ptrs_, sizeof(DevPtrs)));
     CUDA_CHECK(cudaMalloc(&d_sortctl_, sizeof(SortCtl)));
     CUDA_CHECK(cudaMalloc(&d_opcnt_, 2 * RIES_MAX_SYMS * sizeof(u64)));
-    CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(PassOut)));
+    CUDA_CHECK(cudaHostAlloc(&h_out_, sizeof(PassOut), cudaHostAllocMapped));
+    memset(h_out_, 0, sizeof(PassOut));
+    CUDA_CHECK(cudaHostGetDevicePointer((void**)&d_host_out_, h_out_, 0));
+    poll_host_ = getenv("RIES_NO_HOST_POLL") == 0; /* test hook: copy + synchronise per pass instead */
     h_ctl_ = &h_out_->ctl;
     h_head_ = h_out_->head;
     CUDA_CHECK(cudaMallocHost(&h_passin_, passin_bytes));
@@ -276,7 +280,7 @@ class DeviceEngine : public Engine {
       h_args_->nforms = (int)nforms; h_args_->best_match0 = best_match0;
       h_args_->cap_nodes = (u32)std::min<size_t>(nodes_.cap, 0xffffffffu);
       h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
-      h_args_->cap_events = (u32)events_.cap; h_args_->pad = 0;
+      h_args_->cap_events = (u32)events_.cap; h_args_->seq = ++pass_seq_;
       /* size class from the previous pass of the same side (sizes grow ~1.3-1.6x per complexity step) */
       int small = (prev_nodes_[using_x ? 1 : 0] <= 12000 && prev_done_[using_x ? 1 : 0] <= 3000) ? 1 : 0;
       if (small && !no_small_post && prev_done_[using_x ? 1 : 0] <= SP_CAP / 3 && nt_ <= 200000u) small = 2;
@@ -299,22 +303,16 @@ class DeviceEngine : public Engine {
       if (tiny) {
         if (host_prof_) hp_t1 = now_us();
         launch_tiny();
-        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
         if (host_prof_) hp_t2 = now_us();
-        CUDA_CHECK(cudaStreamSynchronize(st_));
+        wait_pass();
         if (host_prof_) hp_t3 = now_us();
-        CUDA_CHECK(cudaGetLastError());
-        d2h_bytes += sizeof(PassOut);
         collect_stamp_times();
       } else if (!shard) {
         if (host_prof_) hp_t1 = now_us();
         launch_stages(0, 3, max_len, small);
-        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
         if (host_prof_) hp_t2 = now_us();
-        CUDA_CHECK(cudaStreamSynchronize(st_));
+        wait_pass();
         if (host_prof_) hp_t3 = now_us();
-        CUDA_CHECK(cudaGetLastError());
-        d2h_bytes += sizeof(PassOut);
         collect_stamp_times();
       } else {
         size_t want_nodes = nodes_.cap, want_done = done_.cap;
@@ -327,10 +325,10 @@ class DeviceEngine : public Engine {
         sharded_passes++;
         was_sharded = true;
         launch_stages(1, 3, max_len, small, true);
-        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(PassOut), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, offsetof(PassOut, seq), cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
         CUDA_CHECK(cudaGetLastError());
-        d2h_bytes += sizeof(PassOut);
+        d2h_bytes += offsetof(PassOut, seq);
         collect_stage_times(1, 3);
         if (gather_pending_) {
           float ms = 0;
@@ -523,6 +521,42 @@ class DeviceEngine : public Engine {
     }
   }
 
+  /* Results of the pass just enqueued.  The last kernel of a pass writes them into the mapped host block and
+     then posts the pass number; the host polls for it (no copy operation, no stream synchronisation), looking
+     at the stream now and then so that a faulted kernel is reported instead of waited for. */
+  void wait_pass() {
+    if (poll_host_) {
+      volatile u32* seq = &h_out_->seq;
+      const u32 want = pass_seq_;
+      for (unsigned spins = 1;; spins++) {
+        if (*seq == want) break;
+        if ((spins & 0xfffu) == 0) {
+          const cudaError_t q = cudaStreamQuery(st_);
+          if (q == cudaSuccess) {
+            if (*seq == want) break;
+            /* the stream is idle and nothing was posted: fall back to the explicit copy */
+            CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, offsetof(PassOut, seq), cudaMemcpyDeviceToHost, st_));
+            CUDA_CHECK(cudaStreamSynchronize(st_));
+            break;
+          }
+          if (q != cudaErrorNotReady) CUDA_CHECK(q);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      __sync_synchronize();
+      u32 ne = h_ctl_->n_events;
+      if (ne > HEAD_EVENTS) ne = HEAD_EVENTS;
+      d2h_bytes += offsetof(PassOut, head) + (unsigned long long)ne * sizeof(MatchEvent) + 4;
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, offsetof(PassOut, seq), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      CUDA_CHECK(cudaGetLastError());
+      d2h_bytes += offsetof(PassOut, seq);
+    }
+  }
+
   /* A pass predicted tiny: three direct launches (tiny_pass.cuh). */
   void launch_tiny() {
     bump_epoch();
@@ -696,6 +730,7 @@ class DeviceEngine : public Engine {
     h.form_first = form_[0].p; h.form_cnt = form_[1].p; h.form_base = form_[2].p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.events = events_.p; h.tiles = tiles_.p; h.staged = staged_.p;
     h.rs_state = rs_state_.p; h.cc_state = cc_state_.p; h.sortctl = d_sortctl_; h.opcnt = d_opcnt_;
+    h.host_out = d_host_out_;
     CUDA_CHECK(cudaMemcpyAsync(d_ptrs_, h_ptrs_, sizeof(DevPtrs), cudaMemcpyHostToDevice, st_));
     ptrs_dirty_ = false;
   }
@@ -718,6 +753,9 @@ class DeviceEngine : public Engine {
   TestTables h_tt_;
   PassOut* d_out_ = 0;
   PassOut* h_out_ = 0;
+  PassOut* d_host_out_ = 0; /* device address of h_out_ (mapped) */
+  u32 pass_seq_ = 0;
+  bool poll_host_ = true;
   PassCtl* d_ctl_ = 0; /* = &d_out_->ctl */
   PassCtl* h_ctl_ = 0;
   unsigned char* d_passin_ = 0; /* PassArgs, then the forms */
