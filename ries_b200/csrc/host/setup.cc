@@ -157,6 +157,36 @@ void parse_args(int argc, char** argv, Options& o, const Sink& out) {
       break;
     } else if (strcmp(a, "-") == 0) {
       /* null option */
+    } else if (strcmp(a, "--min-memory") == 0) { /* ries.c:11559 */
+      /* steers only the reference's thrash watchdog (4768-4830), which stops a search that has become slow for
+         lack of RAM: a matter of wall-clock time on the host, with no counterpart here.  The notice is printed. */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t)) {
+        out.printf("Memory-hogging safeguard disabled for the first %g bytes.\n", fabs(t));
+      } else {
+        out.printf("%s: --min-memory should be followed by a numeric argument.\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
+    } else if (strcmp(a, "--memory-abort-threshold") == 0) { /* ries.c:11459: same watchdog */
+      const char* v = next_arg();
+      double t;
+      if (v && sscanf(v, "%lf", &t)) {
+        if (t > 1.0) {
+          out.printf("Memory slowness abort ratio: %g.\n", t);
+        } else {
+          out.printf("%s: --memory-abort-threshold should be at least 1.0, and values less than about 1.5 are"
+                     " unlikely to be of much use.\n\n", o.argv0.c_str());
+          brief_help(out);
+          throw ExitRequest{-1};
+        }
+      } else {
+        out.printf("%s: --memory-abort-threshold should be followed by a numeric\n"
+                   "argument larger than 1.0 (larger than 1.5 is recommended).\n\n", o.argv0.c_str());
+        brief_help(out);
+        throw ExitRequest{-1};
+      }
     } else if (strcmp(a, "--canon-reduction") == 0) { /* ries.c:11255 */
       if (i < argc && argv[i] && argv[i][0] && argv[i][0] != '-') {
         const char* v = next_arg();
