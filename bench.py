@@ -377,7 +377,7 @@ def main():
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_per_launch"]
-        traffic_src = "profiles/r1_l6_k_expand_traffic.json: ncu dram__bytes_read.sum+dram__bytes_write.sum over the %d k_expand launches of one search (cold process), per launch" % tj["launches"]
+        traffic_src = "profiles/r1_l6_k_expand_traffic.json: ncu dram__bytes_read.sum+dram__bytes_write.sum over the %d K1 launches (k_expand + k_tiny_front) of one search (cold process), per launch" % tj["launches"]
     roofline = {
         "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,

@@ -517,7 +517,7 @@ class DeviceEngine : public Engine {
                                  : (stage == 1) ? ((small == 2) ? 1 : 11)
                                  : (stage == 2) ? ((small == 2) ? 1 : 3) : 2;
       kernel_launches += k;
-      stage_launches[stage] += k;
+      stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
     }
   }
 

@@ -26,7 +26,7 @@ for name in os.environ.get("KERNELS", "k_expand k_rs_onesweep k_classify_compact
 PY
 cat $out/${tag}_pick.txt
 # DRAM traffic of every launch of the dominant kernel (for bench.py's roofline.traffic)
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_expand --csv \
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:k_expand|k_tiny_front' --csv \
   --log-file $out/${tag}_k_expand_dram.csv ./ries_b200/bin/ries "$@" > $out/${tag}_ncu2.log 2>&1
 python - "$out/${tag}_k_expand_dram.csv" <<'PY' | tee $out/${tag}_k_expand_traffic.json
 import csv, json, sys
@@ -35,7 +35,7 @@ tot = 0.0; ids = set()
 for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row["Metric Unit"], 1)
     tot += v; ids.add(row["ID"])
-print(json.dumps({"kernel": "k_expand", "launches": len(ids), "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(1, len(ids))}))
+print(json.dumps({"kernel": "k_expand + k_tiny_front (every K1 launch)", "launches": len(ids), "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(1, len(ids))}))
 PY
 while read name idx; do
   timeout 600 ncu --set full --import-source on --clock-control none -s $idx -c 1 -f -o $out/${tag}_${name} \
