@@ -229,7 +229,14 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
           if (lane == 0) b0 = atomicAdd(&s_next, 32u);
           b0 = __shfl_sync(0xffffffffu, b0, 0);
           if (b0 >= T) break;
+#ifndef EXP_FORWARD_BATCHES
+          /* batches from the end of the list first: the list is in slot order and the heavy operators of a class
+             (^ v L A, the trigonometric functions) are its last slots, so they start first and the cheap
+             constants fill the tail of the phase (K1 45.9 -> 44.8 ms at -l6) */
+          const u32 i = (((T + 31u) >> 5) - 1u - (b0 >> 5)) * 32u + lane;
+#else
           const u32 i = b0 + lane;
+#endif
           if (i < T) {
             const u32 it = B.item[i];
             const u32 pl = (it >> 4) & 1023u, k = it & 15u;
