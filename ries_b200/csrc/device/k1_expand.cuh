@@ -124,14 +124,29 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
     if (tid == 0) { s_lvl[0] = ctl->lvl_begin; s_lvl[1] = ctl->lvl_end; s_lvl[2] = ctl->done_count; s_lvl[3] = ctl->overflow; }
     exp_sync<TINY>();
   }
+  const DevPtrs D = *Dp;
+  if (!TINY) {
+    /* Programmatic dependent launch: the launches of one pass follow each other with the attribute set (see
+       enqueue_stage), so this kernel's blocks may start while the previous expression position is still
+       draining.  What does not depend on it -- the search constants -- is fetched first; then the next
+       position is allowed to start its own prologue, and only then do we wait for the previous one to be
+       complete and visible.  (Both instructions are no-ops in a launch without the attribute.) */
+    const u32* src = (const u32*)D.P;
+    u32* dst = (u32*)&P;
+    for (u32 i = tid; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];
+    const u32* tsrc = (const u32*)D.tt;
+    u32* tdst = (u32*)&TT;
+    for (u32 i = tid; i < sizeof(TestTables) / 4; i += EXP_THREADS) tdst[i] = tsrc[i];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   const u32 lvl_begin = TINY ? s_lvl[0] : ctl->lvl_begin, lvl_end = TINY ? s_lvl[1] : ctl->lvl_end;
   const u32 n = lvl_end - lvl_begin;
   const u32 ntiles = (n + EXP_PARENTS - 1) / EXP_PARENTS;
-  const DevPtrs D = *Dp;
   const int using_x = Ap->using_x, cplx = Ap->cplx;
   const u32 cap_nodes = Ap->cap_nodes, cap_done = Ap->cap_done;
   if (ntiles != 0 && !((TINY ? s_lvl[3] : ctl->overflow) & (OVF_NODES | OVF_DONE))) {
-    if (!TINY || first) {
+    if (TINY && first) {
       const u32* src = (const u32*)D.P;
       u32* dst = (u32*)&P;
       for (u32 i = tid; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];

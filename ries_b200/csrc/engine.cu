@@ -135,6 +135,7 @@ class DeviceEngine : public Engine {
     /* tiny passes (tiny_pass.cuh): RIES_NO_TINY switches them off, RIES_TINY_NODES / RIES_TINY_FRONTIER move the
        prediction threshold and the frontier width at which the kernel gives up (test hooks) */
     use_tiny_ = getenv("RIES_NO_TINY") == 0;
+    use_pdl_ = getenv("RIES_NO_PDL") == 0; /* test hook: plain stream order between the K1 launches */
     if (const char* e = getenv("RIES_TINY_NODES")) tiny_nodes_ = (u32)strtoul(e, 0, 10);
     if (const char* e = getenv("RIES_TINY_FRONTIER")) tiny_frontier_ = (u32)strtoul(e, 0, 10);
     CUDA_CHECK(cudaFuncSetAttribute(k_tiny_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TINY_DYN_SMEM));
@@ -448,7 +449,18 @@ class DeviceEngine : public Engine {
     switch (stage) {
       case 0:
         k_pass_begin<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-        for (int lvl = 0; lvl < max_len; lvl++) k_expand<<<g_exp, EXP_THREADS, EXP_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_);
+        for (int lvl = 0; lvl < max_len; lvl++) {
+          /* positions after the first may overlap their prologue with the previous position's tail
+             (programmatic dependent launch; the kernel waits on the dependency itself) */
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(g_exp); cfg.blockDim = dim3(EXP_THREADS); cfg.dynamicSmemBytes = EXP_DYN_SMEM; cfg.stream = st_;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at; cfg.numAttrs = (use_pdl_ && lvl > 0) ? 1 : 0;
+          const DevPtrs* a0 = d_ptrs_; const PassArgs* a1 = d_args_; PassCtl* a2 = d_ctl_;
+          CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_expand, a0, a1, a2));
+        }
         break;
       case 1:
         if (small == 2) {
@@ -739,7 +751,7 @@ class DeviceEngine : public Engine {
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
-  bool use_tiny_ = true, host_prof_ = false;
+  bool use_tiny_ = true, host_prof_ = false, use_pdl_ = true;
   double hp_[6] = {0, 0, 0, 0, 0, 0}; /* prepare, enqueue, wait, collect, events, passes */
   static double now_us() {
     struct timespec ts;
