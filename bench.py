@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--workload", default="search", choices=["search", "batch"],
                     help="search: one full-depth search per step (default); batch: BASELINE config 5, many targets")
     ap.add_argument("--batch-size", type=int, default=256, help="targets per step over all ranks (batch workload)")
-    ap.add_argument("--workers", type=int, default=4, help="concurrent engines per GPU (batch workload)")
+    ap.add_argument("--workers", type=int, default=8, help="concurrent engines per GPU (batch workload)")
     ap.add_argument("--shard-search", action="store_true",
                     help="N>1: all ranks work on ONE search (K1 sharded by forms, NCCL all-gather of the complete "
                          "expressions; strong scaling) instead of one independent target per rank")
