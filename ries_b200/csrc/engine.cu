@@ -232,6 +232,9 @@ class DeviceEngine : public Engine {
     sharded_passes = gather_bytes = 0;
     tiny_passes = 0;
     gather_ms = 0;
+    /* cross-check mode (bench.py): the stages of every pass bracketed by CUDA events on this stream, as before the
+       device clock stamps; tiny passes go through the general kernels so that the stages stay separable */
+    stage_events_ = getenv("RIES_STAGE_EVENTS") != 0;
   }
 
   long inserted_before(uint32_t seq, bool inclusive) override {
@@ -296,7 +299,7 @@ class DeviceEngine : public Engine {
       h_args_->pad2 = 0;
       if (shard && small == 2) small = 1; /* the single-block kernel has no local/global split */
       /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh) */
-      const bool tiny = use_tiny_ && small == 2 && !force_small_post_ && !shard &&
+      const bool tiny = use_tiny_ && !stage_events_ && small == 2 && !force_small_post_ && !shard &&
                         prev_nodes_[using_x ? 1 : 0] <= tiny_nodes_;
       CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                  cudaMemcpyHostToDevice, st_));
@@ -310,11 +313,12 @@ class DeviceEngine : public Engine {
         collect_stamp_times();
       } else if (!shard) {
         if (host_prof_) hp_t1 = now_us();
-        launch_stages(0, 3, max_len, small);
+        launch_stages(0, 3, max_len, small, stage_events_);
         if (host_prof_) hp_t2 = now_us();
         wait_pass();
+        if (stage_events_) CUDA_CHECK(cudaStreamSynchronize(st_)); /* the last event must have completed */
         if (host_prof_) hp_t3 = now_us();
-        collect_stamp_times();
+        if (stage_events_) collect_stage_times(0, 3); else collect_stamp_times();
       } else {
         size_t want_nodes = nodes_.cap, want_done = done_.cap;
         const u32 fovf = sharded_front(max_len, small, &want_nodes, &want_done, &gen_k1);
@@ -751,7 +755,7 @@ class DeviceEngine : public Engine {
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
-  bool use_tiny_ = true, host_prof_ = false, use_pdl_ = true;
+  bool use_tiny_ = true, host_prof_ = false, use_pdl_ = true, stage_events_ = false;
   double hp_[6] = {0, 0, 0, 0, 0, 0}; /* prepare, enqueue, wait, collect, events, passes */
   static double now_us() {
     struct timespec ts;
