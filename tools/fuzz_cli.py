@@ -69,6 +69,13 @@ def cases(n, seed):
         t = target()
         args = flags()
         args.insert(rng.randint(0, len(args)), t)
+        # options added later draw from a stream of their own, so that the case lists of the seeds the test suites
+        # pin (tests/test_oracle_cpu.py, tests/test_gpu_parity.py) stay what they were apart from the additions
+        r2 = random.Random(" ".join(args))
+        if r2.random() < 0.03:
+            k = r2.randint(0, len(args)); args[k:k] = ["--min-memory", r2.choice(["1e6", "0", "-3e9"])]
+        if r2.random() < 0.03:
+            k = r2.randint(0, len(args)); args[k:k] = ["--memory-abort-threshold", r2.choice(["1.5", "3", "1.0", "x"])]
         out.append(args)
     return out
 
