@@ -6,14 +6,18 @@ through the reference-facing C ABI (`ries_main(argc, argv, write_cb)`, include/r
 the call the web worker makes (`callMain([...flags, target])`).  Nothing is reused between steps except
 device allocations: every step rebuilds the whole value table from scratch.
 
-    python bench.py --gpus 1 --steps 3 --warmup 3
-    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N independent targets)
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+        N>1: ONE search over the N GPUs (strong scaling); every rank's report is compared with the reference's
     python bench.py --impl reference          (the reference's own CPU implementation, oracle/_ref/ries)
 
-Default workload (N=1): `ries 2.5063141592653589 -l6 -F3`, the full-depth -l6 search BASELINE.json's metric
-is quoted on (1.45e8 expressions, 2.04e9 dead-ends, 3.23e7 table rows; fits one GPU).
+Workload (every N): `ries 2.5063141592653589 -l6 -F3`, the full-depth -l6 search BASELINE.json's metric is
+quoted on (1.45e8 expressions, 2.04e9 dead-ends, 3.23e7 table rows; fits one GPU).  The N=1 line also carries
+BASELINE configs 1, 2, 3, 4 (one timing each, report checked against the reference's committed output) and
+config 5 (a batch of targets at -l4, with an 8-process CPU sample beside it).
 """
 import argparse
+import hashlib
 import json
 import os
 import re
@@ -27,19 +31,29 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_TARGET = "2.5063141592653589"
 DEFAULT_LEVEL = "6"
-# BASELINE.md config 5 distribution: f"{random.uniform(0,10):.6f}", seed 20261019 (first 8 targets)
+# BASELINE.md config 5 distribution: f"{random.uniform(0,10):.6f}", seed 20261019
 BATCH_SEED = 20261019
 
-# algorithmic bytes per survivor through the sort (read once + write once of a
-# 32-byte row) and per merged row (read old+new, write merged); flop weights per exec'd symbol.
+# ALGORITHMIC bytes.  K1 must write every complete expression once (32 B row + 2 B
+# form index); the sort reads and writes each 32 B row once (64 B/key, whatever the number of digit passes);
+# merge + neighbour search: read old + new, write merged (2 x 32 B) + one read of the merged table (32 B).
 ROW_BYTES = 32
-NODE_BYTES = 48
+K1_BYTES_PER_EXPR = ROW_BYTES + 2
 SORT_BYTES_PER_KEY = 2 * ROW_BYTES
-MERGE_BYTES_PER_ROW = 2 * ROW_BYTES
+MERGE_BYTES_PER_ROW = 3 * ROW_BYTES
 # fp64 flops per exec() of each symbol: (value, extra for d/dx), SURVEY.md section 8(d)
 FLOP_WEIGHTS = {"n": (1, 1), "s": (1, 2), "r": (1, 3), "q": (1, 2), "+": (7, 1), "-": (7, 1), "*": (1, 3), "/": (1, 5),
                 "l": (25, 1), "E": (20, 1), "S": (50, 3), "C": (50, 3), "T": (45, 4), "^": (60, 30), "v": (62, 32),
                 "L": (52, 8), "A": (45, 7)}
+
+# the other BASELINE.json configs, timed once each on the N=1 line: (key, golden case name, argv)
+SIDE_CONFIGS = [
+    ("config1_default_level", "pi_l2_F3", ["3.14159265358979", "-F3"]),
+    ("config2_l4", "t25063_l4_F3", ["2.5063", "-l4", "-F3"]),
+    ("config3_phi_l6_early_exit", "phi_l6_early_exit", None),
+    ("config4_i_l5", "l5i", ["143", "-i", "-l5", "-F3"]),
+    ("config4_S_l5", "l5S", ["2.5063", "-l5", "-S1234+-*/x", "-F3"]),
+]
 
 
 def peaks():
@@ -47,8 +61,33 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d.get("hbm_gbs", 6650.0)), "measured"
-    return 6650.0, "fallback"
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def normalise(text, prog=None):
+    text = re.sub(r"Time: [0-9.]+", "Time: X", text)
+    return text.replace(prog, "ries") if prog else text
+
+
+def golden_args(name):
+    with open(os.path.join(ROOT, "tests", "golden", "cases.json")) as f:
+        for c in json.load(f):
+            if c["name"] == name:
+                return c["args"]
+    return None
+
+
+def golden_text(name):
+    p = os.path.join(ROOT, "tests", "golden", name + ".txt")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return f.read()
+
+
+def shown_status(code):
+    return code & 0xff if code != 0 else 0
 
 
 class ClockSampler(threading.Thread):
@@ -87,11 +126,11 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+# ------------------------------------------------------------------------------------- the CPU side
 def ref_binary():
-    for name in ("ries",):
-        p = os.path.join(ROOT, "oracle", "_ref", name)
-        if os.path.exists(p):
-            return p, "reference"
+    p = os.path.join(ROOT, "oracle", "_ref", "ries")
+    if os.path.exists(p):
+        return p, "reference"
     p = os.path.join(ROOT, "oracle", "_build", "ries_oracle")
     return (p, "port") if os.path.exists(p) else (None, None)
 
@@ -106,7 +145,96 @@ def run_cpu(binary, argv):
     t0 = time.perf_counter()
     r = subprocess.run([binary] + argv + ["--no-slow-messages"], env=env, capture_output=True, text=True)
     dt = time.perf_counter() - t0
-    return parse_expressions(r.stdout), dt
+    return parse_expressions(r.stdout), dt, r.stdout, r.returncode
+
+
+def boot_id():
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            return f.read().strip()
+    except OSError:
+        return "unknown"
+
+
+def cpu_cache_path(binary, argv):
+    h = hashlib.sha1((binary + "\0" + "\0".join(argv)).encode()).hexdigest()[:16]
+    return os.path.join("/tmp", "ries_b200_cpu_%s.json" % h)
+
+
+def cpu_full_run(binary, kind, argv, allow_cache=True):
+    """The reference's CPU implementation on the headline command line, run to completion ONCE on one host
+    core (it is single-threaded).  The measurement is kept in /tmp keyed by (binary, argv) and this boot, so
+    that the other bench invocations of the same session on the same box (N=2,4,8 of a scaling run; the B200
+    arm's cpu_baseline) quote the same run instead of spending another 5-8 minutes each."""
+    path = cpu_cache_path(binary, argv)
+    if allow_cache and os.path.exists(path):
+        try:
+            with open(path) as f:
+                c = json.load(f)
+            if c.get("boot_id") == boot_id() and time.time() - c.get("when", 0) < 6 * 3600:
+                c["cached"] = True
+                return c
+        except (OSError, ValueError):
+            pass
+    n, dt, text, rc = run_cpu(binary, argv)
+    gname = "l6full" if argv[:3] == [DEFAULT_TARGET, "-l" + DEFAULT_LEVEL, "-F3"] else None
+    gold = golden_text(gname) if gname else None
+    c = {"expressions": n, "seconds": dt, "returncode": rc, "kind": kind, "argv": argv, "boot_id": boot_id(),
+         "when": time.time(), "cached": False,
+         "identical_to_golden": (normalise(text, binary) + "exit=%d\n" % rc == gold) if gold else None}
+    try:
+        with open(path, "w") as f:
+            json.dump(c, f)
+    except OSError:
+        pass
+    return c
+
+
+def cpu_bounded_prefix(binary, argv, seconds):
+    """A bounded sample of the SAME command: the reference runs with its own per-pass trace (-Dy) on a pty
+    (line-buffered), is stopped after `seconds`, and the expressions it had generated at its last completed
+    pass are divided by the time of that line.  (Expression rate falls with depth -- the tree grows -- so a
+    prefix flatters the CPU; the full run of `--impl reference` is the same-config figure.)"""
+    import pty
+    env = dict(os.environ, HOME="/nonexistent")
+    master, slave = pty.openpty()
+    t0 = time.perf_counter()
+    p = subprocess.Popen([binary] + argv + ["-Dy", "--no-slow-messages"], env=env, stdout=slave, stderr=subprocess.DEVNULL)
+    os.close(slave)
+    buf = b""
+    best = (0.0, 0.0)
+    done = False
+    try:
+        while True:
+            now = time.perf_counter() - t0
+            if now > seconds:
+                break
+            import select
+            r, _, _ = select.select([master], [], [], max(0.05, min(1.0, seconds - now)))
+            if not r:
+                if p.poll() is not None:
+                    done = True
+                    break
+                continue
+            try:
+                chunk = os.read(master, 65536)
+            except OSError:
+                done = True
+                break
+            if not chunk:
+                done = True
+                break
+            buf += chunk
+            stamp = time.perf_counter() - t0
+            for m in re.finditer(rb"gen_total ([0-9.e+]+) \(", buf):
+                best = (float(m.group(1)), stamp)
+            buf = buf[-4096:]
+    finally:
+        if p.poll() is None:
+            p.kill()
+        p.wait()
+        os.close(master)
+    return {"expressions": best[0], "seconds": best[1], "ran_to_completion": done}
 
 
 def targets_for(n):
@@ -120,53 +248,60 @@ def targets_for(n):
     return out
 
 
-def batch_workload(args, rank, local_rank, world, dist, torch, ries_b200):
-    """BASELINE config 5: targets ~ U(0,10) with 6 decimals (seed 20261019) at -l<level>, sharded round-robin
-    over ranks, `--workers` concurrent engines per GPU.  A step = the whole batch once."""
-    from ries_b200.parallel import shard_targets
-    level = args.level if args.level != DEFAULT_LEVEL else "4"
-    mine = shard_targets(targets_for(args.batch_size), rank, world)
-    flags = ["-l" + level, "-F3", "--no-slow-messages"]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    for _ in range(args.warmup):
-        ries_b200.batch(mine[:max(2 * args.workers, 8)], flags, workers=args.workers)
-    barrier()
+def cpu_batch_sample(binary, level, n=8):
+    """the reference has no batch mode -> n concurrent processes, one target each."""
+    env = dict(os.environ, HOME="/nonexistent")
+    ts = targets_for(n)
     t0 = time.perf_counter()
-    exprs = 0
-    for _ in range(args.steps):
-        for code, text in ries_b200.batch(mine, flags, workers=args.workers):
-            exprs += parse_expressions(text)
-    barrier()
-    wall = time.perf_counter() - t0
+    ps = [subprocess.Popen([binary, t, "-l" + level, "-F3", "--no-slow-messages"], env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, text=True) for t in ts]
+    exprs = sum(parse_expressions(p.communicate()[0]) for p in ps)
+    dt = time.perf_counter() - t0
+    return {"targets": n, "processes": n, "cores": min(n, os.cpu_count() or n), "seconds": dt,
+            "targets_per_sec": n / dt, "expr_per_sec": exprs / dt,
+            "sample": "the first %d targets of the batch, one reference process each, all at once" % n}
+
+
+# ------------------------------------------------------------------------------------- B200 arm pieces
+def batch_object(args, ries_b200, rank, world, dist, torch):
+    """BASELINE config 5: targets ~ U(0,10) with 6 decimals (seed 20261019) at -l4 through ries_batch; the first
+    64 reports are compared with the reference's (tests/golden/batch_l4.json, made by tools/make_batch_golden.py)."""
+    from ries_b200.parallel import shard_targets
+    level = args.batch_level
+    alltargets = targets_for(args.batch_size)
+    mine = shard_targets(alltargets, rank, world)
+    flags = ["-l" + level, "-F3", "--no-slow-messages"]
+    ries_b200.batch(mine[:max(2 * args.workers, 8)], flags, workers=args.workers)  # warm-up: engines, graphs
     if dist is not None:
-        t = torch.tensor([float(exprs), float(len(mine) * args.steps)], dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        dist.barrier()
+    t0 = time.perf_counter()
+    got = ries_b200.batch(mine, flags, workers=args.workers)
+    wall = time.perf_counter() - t0
+    exprs = sum(parse_expressions(text) for _, text in got)
+    checked, same = 0, 0
+    gpath = os.path.join(ROOT, "tests", "golden", "batch_l%s.json" % level)
+    if os.path.exists(gpath):
+        with open(gpath) as f:
+            g = json.load(f)
+        want = dict(zip(g["targets"], g["reports"]))
+        for t, (code, text) in zip(mine, got):
+            if t in want:
+                checked += 1
+                same += int(normalise(text) + "exit=%d\n" % shown_status(code) == want[t])
+    nt = float(len(mine))
+    if dist is not None:
+        t = torch.tensor([exprs, nt, checked, same], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         tm = torch.tensor([wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        exprs_all, searches_all = t.tolist()
-        wall_all = tm.item()
-    else:
-        exprs_all, searches_all, wall_all = float(exprs), float(len(mine) * args.steps), wall
-    if rank == 0:
-        print(json.dumps({
-            "metric": "expressions_evaluated_per_sec", "value": exprs_all / wall_all, "unit": "expr/s",
-            "n_gpus": max(args.gpus, world), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * wall_all / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batch of %d targets U(0,10) 6dp seed %d, ries <t> -l%s -F3, %d engines per GPU"
-                                   % (args.batch_size, BATCH_SEED, level, args.workers)},
-            "targets_per_sec": searches_all / wall_all,
-            "e2e": {"value": exprs_all / wall_all, "unit": "expr/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-                    "api": "ries_batch(targets, flags, workers, done_cb) via ctypes"},
-        }))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+        exprs, nt, checked, same = t.tolist()
+        wall = tm.item()
+    return {"workload": "BASELINE config 5: %d targets U(0,10) 6dp seed %d, `ries <t> -l%s -F3`, %d engines per GPU, "
+                        "%d GPU(s)" % (args.batch_size, BATCH_SEED, level, args.workers, world),
+            "targets": int(nt), "seconds": wall, "targets_per_sec": nt / wall, "targets_per_sec_per_gpu": nt / wall / world,
+            "expr_per_sec": exprs / wall, "reports_checked_against_reference": int(checked),
+            "reports_identical": int(same), "api": "ries_batch(targets, flags, workers, done_cb) via ctypes"}
 
 
 def main():
@@ -177,15 +312,18 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--target", default=DEFAULT_TARGET)
     ap.add_argument("--level", default=DEFAULT_LEVEL)
-    ap.add_argument("--cpu-level", default="4", help="level of the bounded CPU sample (same target)")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=25.0,
+                    help="length of the bounded CPU sample when no full reference run of this box is on record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the side configs and the batch object")
     ap.add_argument("--workload", default="search", choices=["search", "batch"],
-                    help="search: one full-depth search per step (default); batch: BASELINE config 5, many targets")
-    ap.add_argument("--batch-size", type=int, default=256, help="targets per step over all ranks (batch workload)")
-    ap.add_argument("--workers", type=int, default=8, help="concurrent engines per GPU (batch workload)")
-    ap.add_argument("--shard-search", action="store_true",
-                    help="N>1: all ranks work on ONE search (K1 sharded by forms, NCCL all-gather of the complete "
-                         "expressions; strong scaling) instead of one independent target per rank")
+                    help="search: one full-depth search per step (default); batch: BASELINE config 5 as the headline")
+    ap.add_argument("--batch-size", type=int, default=256, help="targets over all ranks (batch object / workload)")
+    ap.add_argument("--batch-level", default="4")
+    ap.add_argument("--workers", type=int, default=8, help="concurrent engines per GPU (batch)")
+    ap.add_argument("--independent-targets", action="store_true",
+                    help="N>1: one independent target per rank (weak scaling, no collective) instead of ONE search "
+                         "over the N GPUs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,8 +331,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_gpus = max(args.gpus, world)
     workload = "ries %s -l%s -F3" % (args.target, args.level)
-    sample_desc = ("the first pass-prefix of the same search: `ries %s -l%s` (identical pass sequence, stops at "
-                   "the -l%s expression budget)" % (args.target, args.cpu_level, args.cpu_level))
+    head_argv = [args.target, "-l" + args.level, "-F3"]
+    is_headline = args.target == DEFAULT_TARGET and args.level == DEFAULT_LEVEL
+    head_golden = golden_text("l6full") if is_headline else None
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -204,21 +343,19 @@ def main():
         if binary is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ries and oracle/_build/ries_oracle are both missing"}))
             return 0
-        argv = [args.target, "-l" + args.cpu_level, "-F3"]
-        for _ in range(min(args.warmup, 1)):
-            run_cpu(binary, argv)
-        total_expr, total_t = 0, 0.0
-        for _ in range(args.steps):
-            n, dt = run_cpu(binary, argv)
-            total_expr += n
-            total_t += dt
-        v = total_expr / total_t
+        c = cpu_full_run(binary, kind, head_argv)
+        v = c["expressions"] / c["seconds"]
+        sample = ("the whole search, run to completion once on one host core (the reference is single-threaded); "
+                  "--steps/--warmup do not apply: steps_effective 1" + (", quoted from this box's earlier run of the same command" if c["cached"] else ""))
         line = {
             "impl": "reference", "metric": "expressions_evaluated_per_sec", "value": v, "unit": "expr/s",
-            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample_desc},
-            "cpu_baseline": {"value": v, "unit": "expr/s", "cores": 1, "kind": kind, "sample": sample_desc},
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "steps_effective": 1, "warmup_effective": 0,
+            "ms_per_step": 1e3 * c["seconds"], "time_to_full_report_s": c["seconds"],
+            "higher_is_better": True, "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "same_config_as_b200_arm": True, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "expr/s", "cores": 1, "kind": c["kind"], "sample": sample,
+                             "seconds": c["seconds"], "expressions": c["expressions"], "cached": c["cached"],
+                             "identical_to_golden": c.get("identical_to_golden")},
             "e2e": {"value": v, "unit": "expr/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -234,8 +371,25 @@ def main():
     os.environ["RIES_DEVICE"] = str(local_rank)
     import ries_b200
 
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     if args.workload == "batch":
-        return batch_workload(args, rank, local_rank, world, dist, torch, ries_b200)
+        b = batch_object(args, ries_b200, rank, world, dist, torch)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "expressions_evaluated_per_sec", "value": b["expr_per_sec"], "unit": "expr/s",
+                "n_gpus": n_gpus, "steps": 1, "warmup": 1, "ms_per_step": 1e3 * b["seconds"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": b["workload"]}, "batch": b,
+                "e2e": {"value": b["expr_per_sec"], "unit": "expr/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                        "api": b["api"]}}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     def join_search_communicator():
         """ries_dist_init on every rank: the id comes from rank 0 over torch.distributed (plumbing only)."""
@@ -245,8 +399,8 @@ def main():
         dist.broadcast(uid, 0)
         ries_b200.dist_init(rank, world, uid.cpu().numpy().tobytes())
 
-    sharded = args.shard_search and world > 1
-    if sharded:
+    one_search = world > 1 and not args.independent_targets
+    if one_search:
         join_search_communicator()
         target = args.target
     elif world > 1:
@@ -255,19 +409,13 @@ def main():
         target = args.target
     argv = [target, "-l" + args.level, "-F3", "--no-slow-messages"]
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step():
+    def step(av=argv):
         t0 = time.perf_counter()
-        code, text = ries_b200.call_main(argv)
+        code, text = ries_b200.call_main(av)
         dt = time.perf_counter() - t0
         st = ries_b200.last_stats()
         assert code in (0, -9998), (code, text[-400:])
-        return dt, st, text
+        return dt, st, text, code
 
     for _ in range(args.warmup):
         step()
@@ -282,11 +430,25 @@ def main():
     wall = time.perf_counter() - t_begin
     clocks = sampler.stop()
 
+    # every timed step's report against the reference's (committed golden, made from the unmodified ries.c)
+    identical = None
+    if head_golden is not None and (world == 1 or one_search):
+        ok = all(normalise(s[2]) + "exit=%d\n" % shown_status(s[3]) == head_golden for s in per_step)
+        if dist is not None:
+            f = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            ok = bool(f.item())
+            h = int(hashlib.sha1(normalise(per_step[-1][2]).encode()).hexdigest()[:12], 16)
+            hs = torch.tensor([h, -h], dtype=torch.int64, device="cuda")
+            dist.all_reduce(hs, op=dist.ReduceOp.MAX)
+            ok = ok and (hs[0].item() == -hs[1].item())  # max == min: every rank printed the same bytes
+        identical = ok
+
     # Cross-check of the per-stage device times: the engine takes them from device clock stamps (%globaltimer)
     # that the first kernel of every stage leaves in the pass's control block; here a few extra steps, outside
     # the timed region, bracket every stage with CUDA events on the engine's stream instead (RIES_STAGE_EVENTS).
     event_check = None
-    if world == 1 and not sharded:
+    if world == 1:
         try:
             os.environ["RIES_STAGE_EVENTS"] = "1"
             ev_steps = [step() for _ in range(3)]
@@ -308,43 +470,16 @@ def main():
     d2h = sum(s[1]["d2h_bytes"] for s in per_step) / args.steps
     sort_keys = sum(s[1]["sort_keys"] for s in per_step)
     merge_rows = sum(s[1]["merge_rows"] for s in per_step)
-    nodes = sum(s[1]["expand_nodes"] for s in per_step)
     dev_total_s = sum(dev_ms) / 1e3
-
-    # N>1, default mode: after the independent-target steps, the same ranks also time ONE search together
-    # (north_star's "time-to-full-report at -l6 on N GPUs"); reported beside the weak-scaling value
-    sharded_extra = None
-    if dist is not None and not sharded and os.environ.get("RIES_BENCH_NO_SHARDED_EXTRA") is None:
-        join_search_communicator()
-        sargv = [args.target, "-l" + args.level, "-F3", "--no-slow-messages"]
-        for _ in range(2):
-            ries_b200.call_main(sargv)
-        barrier()
-        ts0 = time.perf_counter()
-        for _ in range(args.steps):
-            scode, _stext = ries_b200.call_main(sargv)
-        barrier()
-        swall = time.perf_counter() - ts0
-        sst = ries_b200.last_stats()
-        ries_b200.dist_finalize()
-        tm = torch.tensor([swall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        sexpr = sst["lhs_expressions"] + sst["rhs_expressions"]
-        sharded_extra = {
-            "workload": "ries %s -l%s -F3, ONE search over %d GPUs" % (args.target, args.level, world),
-            "time_to_full_report_s": tm.item() / args.steps, "expr_per_s_e2e": sexpr * args.steps / tm.item(),
-            "sharded_passes": sst["sharded_passes"], "allgather_MB_per_search": sst["gather_bytes"] / 1e6, "allgather_ms": sst["gather_ms"],
-            "stage_ms": sst["stage_ms"], "scaling": "strong",
-            "how": "forms dealt round-robin to ranks for K1; each rank sorts and pre-dedupes its own expressions "
-                   "against its table replica; the kept rows are all-gathered rank-major over NCCL; the final "
-                   "sort/dedupe/match/merge run replicated; every rank prints the identical report",
-        }
+    last = per_step[-1][1]
 
     # whole-job numbers: sum of units over ranks, max of time over ranks
     if dist is not None:
-        if sharded:  # every rank holds the totals of the one search: count them once
-            exprs, dead = (exprs, dead) if rank == 0 else (0.0, 0.0)
-        t = torch.tensor([exprs, dead, float(launches)], dtype=torch.float64, device="cuda")
+        if one_search:  # every rank holds the totals of the one search: count them once
+            exprs_c, dead_c = (exprs, dead) if rank == 0 else (0.0, 0.0)
+        else:
+            exprs_c, dead_c = exprs, dead
+        t = torch.tensor([exprs_c, dead_c, float(launches)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         tmax = torch.tensor([wall, dev_total_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -353,29 +488,37 @@ def main():
     else:
         exprs_all, dead_all, launches_all, wall_all, dev_all = exprs, dead, launches, wall, dev_total_s
 
-    if sharded:
+    # N>1: the same ranks also run independent targets (weak scaling, no collective) as a secondary figure
+    independent = None
+    if one_search:
         ries_b200.dist_finalize()
+        if os.environ.get("RIES_BENCH_NO_INDEPENDENT") is None:
+            iargv = [targets_for(world)[rank], "-l" + args.level, "-F3", "--no-slow-messages"]
+            step(iargv)
+            barrier()
+            ti0 = time.perf_counter()
+            isteps = [step(iargv) for _ in range(max(1, min(args.steps, 3)))]
+            barrier()
+            iwall = time.perf_counter() - ti0
+            ie = sum(s[1]["lhs_expressions"] + s[1]["rhs_expressions"] for s in isteps)
+            t = torch.tensor([ie], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            tm = torch.tensor([iwall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            independent = {"workload": "ries <t_rank> -l%s -F3, one independent target per GPU (config-5 distribution), no collective" % args.level,
+                           "scaling": "weak", "expr_per_s_e2e": t.item() / tm.item(), "steps": len(isteps),
+                           "seconds_per_step": tm.item() / len(isteps)}
     if rank != 0:
         if dist is not None:
+            if world > 1 and not args.no_extras and os.environ.get("RIES_BENCH_NO_BATCH") is None:
+                batch_object(args, ries_b200, rank, world, dist, torch)
             dist.destroy_process_group()
         return 0
 
     hbm_peak, peak_kind = peaks()
-    # ---- roofline of the dominant stage (device time from CUDA events on the engine's stream) ----
-    # algorithmic bytes: K1 streams every live prefix once out (48 B) and once in (48 B)
-    # and writes each complete expression once (32 B row + 2 B form); the sort reads and writes each 32 B row
-    # once; the merge reads old+new and writes merged (2 x 32 B per merged row) + one 32 B neighbour read.
-    k1_bytes = nodes * 2 * NODE_BYTES + sort_keys * (ROW_BYTES + 2)
-    sort_bytes = sort_keys * SORT_BYTES_PER_KEY
-    merge_bytes = merge_rows * MERGE_BYTES_PER_ROW + merge_rows * ROW_BYTES
-    stages = [
-        ("K1 enumerate+evaluate (k_expand)", k1_bytes, dev_ms[0], dev_launches[0]),
-        ("K2 order+radix sort (k_reorder/k_rs_onesweep)", sort_bytes, dev_ms[1], dev_launches[1]),
-        ("K2/K3 classify+match+merge (k_classify_compact/k_match_merge_new/k_merge_old)", merge_bytes, dev_ms[2], dev_launches[2]),
-    ]
-    dom = max(stages, key=lambda s: s[2])
-    achieved = dom[1] / (dom[2] / 1e3) / 1e9 if dom[2] > 0 else 0.0
-    # K1's fp64 figure: exec() calls per symbol (counted on the device) x SURVEY 8(d) flop weights
+    # ---- roofline of the dominant kernel: K1 (k_expand), fp64-bound by SURVEY 8(d) ----
+    # achieved = algorithmic flop (exec() calls per symbol, counted on the device, x SURVEY 8(d) weights) / K1's
+    # device time; per launch = the same ratio (sum over launches / sum of launch durations)
     flops = 0.0
     execs = 0
     for st in (s[1] for s in per_step):
@@ -385,49 +528,68 @@ def main():
             execs += c["rhs"] + c["lhs"]
     fp64_peak = ries_b200.fp64_peak_tflops()
     fp64_ach = flops / (dev_ms[0] / 1e3) / 1e12 if dev_ms[0] > 0 else 0.0
-    # DRAM traffic of the dominant kernel: not measurable outside a profiler, so it is taken from the committed
-    # ncu capture of this same workload (tools/gpu_profile.sh -> profiles/), per launch like `achieved`
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_l6_k_expand_traffic.json")
-    if dom[0].startswith("K1") and args.workload == "search" and args.target == DEFAULT_TARGET \
-            and args.level == DEFAULT_LEVEL and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_per_launch"]
-        traffic_src = "profiles/r1_l6_k_expand_traffic.json: ncu dram__bytes_read.sum+dram__bytes_write.sum over the %d K1 launches (k_expand + k_tiny_front) of one search (cold process), per launch" % tj["launches"]
+    for tname in ("r2_l6_k_expand_traffic.json", "r1_l6_k_expand_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if is_headline and world == 1 and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_src = ("profiles/%s: ncu dram__bytes_read.sum+dram__bytes_write.sum over the %d K1 launches of one "
+                           "search (cold process), per launch" % (tname, tj["launches"]))
+            break
+
+    def hbm_stage(name, algo_bytes, ms, nlaunch):
+        ach = algo_bytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {"kernels": name, "algorithmic_bytes_per_step": algo_bytes / args.steps, "ms_per_step": ms / args.steps,
+                "launches_per_step": nlaunch / args.steps, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak}
+    k1_algo = exprs * K1_BYTES_PER_EXPR
+    hbm = {
+        "K1_output": hbm_stage("k_expand: 34 B per complete expression it must write", k1_algo, dev_ms[0], dev_launches[0]),
+        "K2_sort": hbm_stage("k_reorder + k_rs_onesweep: 64 B per key", exprs * SORT_BYTES_PER_KEY, dev_ms[1], dev_launches[1]),
+        "K2K3_dedupe_match_merge": hbm_stage("k_classify_compact + k_match_merge_new + k_merge_old: 96 B per merged row",
+                                             merge_rows * MERGE_BYTES_PER_ROW, dev_ms[2], dev_launches[2]),
+        "peak_kind": peak_kind,
+    }
+    if traffic is not None and dev_launches[0]:
+        hbm["K1_output"]["ncu_traffic_over_algorithmic"] = traffic * dev_launches[0] / max(k1_algo, 1.0)
     roofline = {
-        "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
-        "algorithmic_bytes_per_launch": (dom[1] / dom[3]) if dom[3] else None,
-        "algorithmic_bytes_per_step": dom[1] / args.steps, "launches_per_step": dom[3] / args.steps,
-        "avg_launch_ms": dom[2] / dom[3] if dom[3] else None,
+        "bound": "fp64", "kernel": "K1 enumerate+evaluate (k_expand)", "achieved": fp64_ach, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak if fp64_peak else None,
+        "peak_kind": "measured here: DFMA microbenchmark on the engine's stream (MEASURED_PEAKS.json has no fp64 entry; SURVEY 8(d))",
+        "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_flop_per_step": flops / args.steps, "exec_calls_per_step": execs / args.steps,
+        "launches_per_step": dev_launches[0] / args.steps,
+        "avg_launch_ms": dev_ms[0] / dev_launches[0] if dev_launches[0] else None,
         "stage_ms_per_step": {"K1_enum_eval": dev_ms[0] / args.steps, "K2_sort": dev_ms[1] / args.steps,
                               "K2K3_dedupe_match_merge": dev_ms[2] / args.steps, "K4_refine": dev_ms[3] / args.steps},
-        "stage_hbm_frac": {s[0].split(" ")[0] + "_" + str(i): (s[1] / (s[2] / 1e3) / 1e9 / hbm_peak if s[2] > 0 else 0.0)
-                           for i, s in enumerate(stages)},
-        "k1_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": fp64_ach / fp64_peak if fp64_peak else None, "peak_kind": "measured DFMA microbenchmark",
-                    "exec_calls_per_step": execs / args.steps, "algorithmic_flop_per_step": flops / args.steps},
+        "hbm": hbm,
+        "sorted_keys_per_step": sort_keys / args.steps, "expressions_per_step": exprs / args.steps,
         "stage_timing": "device clock stamps (%globaltimer) written by the first kernel of each stage into the pass's control block, on the engine's stream, summed over the timed region",
         "cuda_event_check": event_check,
-        "note": "K1 does ~14 flop per exec() and ~10 integer tests per exec(): it is bound by latency/issue, not by the fp64 pipe or HBM (profiles/); both fractions are given so the distance to either roof is explicit",
+        "note": "K1 does ~14 algorithmic flop and ~10 integer tests per exec(): it is bound by instruction issue and latency, not by the fp64 pipe or HBM (profiles/); both fractions are given so the distance to either roof is explicit",
     }
 
+    mode = ("ONE search over %d GPUs: forms dealt round-robin for K1, hash pre-dedupe + local sort per rank, NCCL "
+            "all-gather of the kept rows, replicated merge; every rank prints the full report" % world)
     line = {
         "metric": "expressions_evaluated_per_sec",
-        "value": exprs_all / dev_all if dev_all > 0 else 0.0,
+        "value": exprs_all / wall_all if wall_all > 0 else 0.0,
         "unit": "expr/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall_all / args.steps,
-        "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong" if one_search else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": workload if world == 1 else (workload + ", ONE search over %d GPUs (K1 sharded by forms, NCCL all-gather)" % world) if sharded else "ries <t_rank> -l%s -F3, one independent target per GPU (BASELINE config-5 distribution, seed %d)" % (args.level, BATCH_SEED),
+            "workload": workload if world == 1 else (workload + ", " + mode) if one_search else "ries <t_rank> -l%s -F3, one independent target per GPU (BASELINE config-5 distribution, seed %d)" % (args.level, BATCH_SEED),
             "expressions_per_step": exprs_all / args.steps, "dead_ends_per_step": dead_all / args.steps,
             "l2": "every step rebuilds all device data from scratch; working set (table + survivors + nodes) exceeds the 126 MB L2 at this level",
-            "value_is": "expressions / device-busy time (device clock stamps over all stages of every pass, cross-checked with CUDA events in roofline.cuda_event_check); e2e is the same search timed around the C-ABI call",
+            "value_is": "expressions / wall time of the timed region (barrier to barrier around the K calls of ries_main, max over ranks). The input of this path is a command line: there is nothing to pre-stage in HBM, so value and e2e are the same measurement; device_busy_expr_per_s is the kernel-only figure",
         },
         "time_to_full_report_s": wall_all / args.steps,
+        "report_identical_to_reference": identical,
+        "device_busy_expr_per_s": exprs_all / dev_all if dev_all > 0 else None,
         "nodes_per_sec_e2e": (exprs_all + dead_all) / wall_all,
         "e2e": {"value": exprs_all / wall_all, "unit": "expr/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "ries_main(argc, argv, write_cb) via ctypes"},
@@ -435,9 +597,14 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
     }
+    if one_search:
+        line["sharded_search"] = {
+            "identical_on_every_rank": identical, "sharded_passes": last["sharded_passes"],
+            "allgather_MB_per_search": last["gather_bytes"] / 1e6, "allgather_ms": last["gather_ms"],
+            "stage_ms": last["stage_ms"], "how": mode}
+    if independent is not None:
+        line["independent_targets"] = independent
 
-    if sharded_extra is not None:
-        line["sharded_search"] = sharded_extra
     if world == 1:
         # SURVEY 8(d) also defines time-to-full-report from PROCESS start: the `ries` binary in a fresh process
         # (CUDA context creation, cold allocations, search, teardown) -- what a command-line user sees; the
@@ -451,15 +618,53 @@ def main():
                                capture_output=True, env=dict(os.environ, RIES_DEVICE=str(local_rank)))
                 cold.append(time.perf_counter() - tc0)
             line["time_to_full_report_cold_process_s"] = min(cold)
+    if not args.no_extras:
+        if world == 1:
+            # the other BASELINE configs: warm call, best of 3, report compared with the reference's
+            for key, gname, cargv in SIDE_CONFIGS:
+                cargv = cargv or golden_args(gname)
+                gold = golden_text(gname)
+                if cargv is None or gold is None:
+                    continue
+                av = list(cargv) + ["--no-slow-messages"]
+                best, same, st = None, True, None
+                for _ in range(4):
+                    t0 = time.perf_counter()
+                    code, text = ries_b200.call_main(av)
+                    dt = time.perf_counter() - t0
+                    same = same and (normalise(text) + "exit=%d\n" % shown_status(code) == gold)
+                    st = ries_b200.last_stats()
+                    best = dt if best is None else min(best, dt)
+                ne = st["lhs_expressions"] + st["rhs_expressions"]
+                line[key] = {"argv": " ".join(cargv), "ms": 1e3 * best, "expressions": ne, "expr_per_s_e2e": ne / best,
+                             "kernel_launches": st["kernel_launches"], "identical_to_reference": same}
+        if os.environ.get("RIES_BENCH_NO_BATCH") is None:
+            line["batch"] = batch_object(args, ries_b200, rank, world, dist, torch)
     if not args.no_cpu_baseline and world == 1:
         binary, kind = ref_binary()
         if binary:
-            n, dt = run_cpu(binary, [args.target, "-l" + args.cpu_level, "-F3"])
-            line["cpu_baseline"] = {"value": n / dt, "unit": "expr/s", "cores": 1, "kind": kind, "sample": sample_desc,
-                                    "seconds": dt, "expressions": n}
+            path = cpu_cache_path(binary, head_argv)
+            if os.path.exists(path):
+                c = cpu_full_run(binary, kind, head_argv)
+                line["cpu_baseline"] = {"value": c["expressions"] / c["seconds"], "unit": "expr/s", "cores": 1, "kind": kind,
+                                        "sample": "the whole search, run to completion on one host core of this box by `bench.py --impl reference` earlier in this session",
+                                        "seconds": c["seconds"], "expressions": c["expressions"]}
+            else:
+                c = cpu_bounded_prefix(binary, head_argv, args.cpu_sample_seconds)
+                if c["seconds"] > 0:
+                    line["cpu_baseline"] = {"value": c["expressions"] / c["seconds"], "unit": "expr/s", "cores": 1, "kind": kind,
+                                            "sample": "the first %.0f s of the same command (`%s -Dy`), expressions generated up to its last completed pass; "
+                                                      "the rate falls with depth (the tree outgrows the caches), so the full run of `--impl reference` (8-9 min) is lower"
+                                                      % (args.cpu_sample_seconds, workload),
+                                            "seconds": c["seconds"], "expressions": c["expressions"]}
+            if not args.no_extras and "batch" in line:
+                line["batch"]["cpu_sample"] = cpu_batch_sample(binary, args.batch_level, 8)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    if identical is False:
+        print("bench.py: the search did not print the reference's report (on every rank)", file=sys.stderr)
+        return 1
     return 0
 
 

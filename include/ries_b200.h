@@ -61,7 +61,9 @@ void ries_last_stats(ries_run_stats *out);
  * run on `n_workers` host threads, each with its own device engine and CUDA stream on the same GPU, so the
  * many small kernels of different searches overlap; results arrive through `done` (serialised, any order),
  * `index` being the position in `targets`.  Returns the number of searches that ended with an error status
- * other than 0 / -9998.  The reference has no batch mode: this is `for t in targets: ries <flags> t`. */
+ * other than 0 / -9998, or -1 (nothing done) while this process is part of a sharded search (ries_dist_init).
+ * The workers' engines are kept for the next call.  The reference has no batch mode: this is
+ * `for t in targets: ries <flags> t`. */
 typedef void (*ries_batch_done_fn)(void *ctx, int index, int exit_code, const char *text, size_t n);
 int ries_batch(int n_targets, const char *const *targets, int n_flags, const char *const *flags,
                int n_workers, ries_batch_done_fn done, void *ctx);

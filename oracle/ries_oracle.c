@@ -260,6 +260,26 @@ static node *root;
 static node *pool; static long pool_left;
 static node *new_node(void) { if (!pool_left) { pool = malloc(sizeof(node) * 65536); pool_left = 65536; } pool_left--; nodes_total++; return pool++; }
 
+/* bt_stats 8399-8428 (called at 12515 under -Dy): node count and average node depth (root = 1), summed in an
+   int like the reference.  Iterative walk: the tree is unbalanced and can be deep. */
+static void bt_stats(void) {
+  long n = 0; int tdepth = 0;
+  static node **stk; static int *dep; static long cap;
+  long sp = 0;
+  if (!cap) { cap = 1 << 16; stk = malloc(cap * sizeof *stk); dep = malloc(cap * sizeof *dep); }
+  if (root) { stk[0] = root; dep[0] = 1; sp = 1; }
+  while (sp) {
+    node *it = stk[--sp]; int d = dep[sp];
+    n++; tdepth += d;
+    if (sp + 2 > cap) { cap *= 2; stk = realloc(stk, cap * sizeof *stk); dep = realloc(dep, cap * sizeof *dep); }
+    if (it->l) { stk[sp] = it->l; dep[sp++] = d + 1; }
+    if (it->r) { stk[sp] = it->r; dep[sp++] = d + 1; }
+  }
+  printf("Current tree stats:\n");
+  printf("       Nodes: %ld\n", n);
+  printf("  Avg. Depth: %f\n", ((double)tdepth) / ((double)n));
+}
+
 static int complexity(const char *e) { int c = 0; for (; *e; e++) c += wgt[(unsigned char)*e]; return c; }
 
 static void defsym_used(const char *e) { for (; *e; e++) if (terse_of[(unsigned char)*e]) def_needed[(unsigned char)*e] = 1; }
@@ -779,17 +799,18 @@ int main(int argc, char **argv) {
         printf("exhaustion timeout (complexity LHS {%d}, RHS {%d}). Possible causes:\n  MAX_ELEN %d too small\n", lmax, rmax, MAXLEN);
         if (NOS_opt) printf("  too many symbols excluded via -N, -O or -S\n");
         if (anagram_opt) printf("  --numeric-anagram too restrictive\n");
-        printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n");
+        printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n"); /* 12504: this restatement has no --derivative-margin option */
         exhausted = 1;
       }
       gen_total = lim_gen;
     }
-    if (debug_y) printf("gen_total %g (lhs %ld rhs %ld) searchmax %g gnm %ld\n", gen_total, lhs_insert, rhs_insert, lim_gen, (long)num_matches);
+    if (debug_y) { printf("gen_total %g (lhs %ld rhs %ld) searchmax %g gnm %ld\n", gen_total, lhs_insert, rhs_insert, lim_gen, (long)num_matches); bt_stats(); }
     if (num_matches == 0 && (debug_y || (now() - t0 > 2.0 && slow_msg))) {
       printf("  Still searching: %11s expr and %.3f sec so far...     \r", pfw(gen_total, 11), now() - t0); fflush(stdout); }
     if (lhs_prune + rhs_prune >= lim_prune) going = 0;
     if (gen_total >= lim_gen) going = 0;
   }
+  if (debug_y) printf("Level %.g search complete (gen_total exceeded lim_gentotal).\n", levadj); /* 12550 */
   if (exhausted) { }
   else if (num_matches == 0) { printf("No solution was found (try using -l%d", (int)floor(levadj + 1.0)); if (init_match_dist < 0.001 * target) printf(" or a larger --max-match-distance"); printf(").  \n"); }
   else if (exact_exit) printf("               No 'exact' solution was found (try using -l%d).\n", (int)floor(levadj + 1.0));

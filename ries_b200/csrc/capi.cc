@@ -1,5 +1,9 @@
 // C ABI (include/ries_b200.h): main(argc, argv) of the reference (ries.c:12062) as a library call.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <exception>
 
 #include <atomic>
 #include <mutex>
@@ -40,6 +44,19 @@ extern "C" int ries_main(int argc, char** argv, ries_write_fn out, void* ctx) {
     code = ries::run_search(opt, *g_engine, sink, &st);
   } catch (const ries::ExitRequest& e) {
     code = e.code;
+    if (code == 1 && g_engine && opt.got_target) { /* out of device memory: start the next call from clean buffers */
+      delete g_engine;
+      g_engine = 0;
+    }
+  } catch (const std::exception& e) { /* nothing may unwind across the C ABI */
+    fprintf(stderr, "ries_b200: %s\n", e.what());
+    code = 3;
+    delete g_engine;
+    g_engine = 0;
+  } catch (...) {
+    code = 3;
+    delete g_engine;
+    g_engine = 0;
   }
   if (g_engine) {
     ries::DeviceReport r;
@@ -79,6 +96,7 @@ extern "C" void ries_last_stats(ries_run_stats* out) {
 extern "C" int ries_dist_unique_id(unsigned char id[128]) { return ries::dist_unique_id(id); }
 
 extern "C" int ries_dist_init(int rank, int world, const unsigned char id[128]) {
+  if (world < 1 || world > RIES_MAX_RANKS || rank < 0 || rank >= world) return -3;
   /* the communicator binds to the current device: select it the way the engine will */
   const char* dev_env = getenv("RIES_DEVICE");
   if (cudaSetDevice(dev_env ? atoi(dev_env) : 0) != cudaSuccess) return -2;
@@ -110,20 +128,44 @@ namespace {
 void append_sink(void* ctx, const char* buf, size_t n) { static_cast<std::string*>(ctx)->append(buf, n); }
 }  // namespace
 
+/* Engines of the batch workers, kept across calls (device buffers, pinned memory, CUDA graphs: building one costs
+   more than a -l2 search).  A worker takes one for the whole call and hands it back at the end. */
+static std::mutex g_pool_mu;
+static std::vector<ries::Engine*> g_pool;
+
+static ries::Engine* pool_take() {
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (!g_pool.empty()) {
+      ries::Engine* e = g_pool.back();
+      g_pool.pop_back();
+      return e;
+    }
+  }
+  try {
+    return ries::make_device_engine();
+  } catch (...) {
+    return 0;
+  }
+}
+
+static void pool_give(ries::Engine* e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  g_pool.push_back(e);
+}
+
 extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags, const char* const* flags,
                           int n_workers, ries_batch_done_fn done, void* ctx) {
   if (n_targets <= 0) return 0;
+  /* the workers' engines would all issue collectives on the one communicator of a sharded search */
+  if (ries::dist_state().world > 1) return -1;
   if (n_workers < 1) n_workers = 1;
   if (n_workers > n_targets) n_workers = n_targets;
   std::atomic<int> next(0), failures(0);
   std::mutex mu;
   auto worker = [&]() {
-    ries::Engine* eng = 0;
-    try {
-      eng = ries::make_device_engine();
-    } catch (const ries::ExitRequest&) {
-      eng = 0;
-    }
+    ries::Engine* eng = pool_take();
     while (true) {
       int i = next.fetch_add(1);
       if (i >= n_targets) break;
@@ -143,13 +185,21 @@ extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags
           code = ries::run_search(opt, *eng, sink, 0);
         } catch (const ries::ExitRequest& e) {
           code = e.code;
+          if (code == 1 && opt.got_target) { /* out of device memory: do not reuse half-grown buffers */
+            delete eng;
+            eng = pool_take();
+          }
+        } catch (...) {
+          code = 3;
+          delete eng;
+          eng = pool_take();
         }
       }
       if (code != 0 && code != RIES_EXIT_NO_ERROR) failures++;
       std::lock_guard<std::mutex> lock(mu);
       if (done) done(ctx, i, code, text.data(), text.size());
     }
-    delete eng;
+    pool_give(eng);
   };
   std::vector<std::thread> pool;
   for (int w = 0; w < n_workers; w++) pool.emplace_back(worker);

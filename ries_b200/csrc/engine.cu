@@ -44,14 +44,22 @@
 
 namespace ries {
 
-#define CUDA_CHECK(x)                                                                        \
-  do {                                                                                       \
-    cudaError_t e_ = (x);                                                                    \
-    if (e_ != cudaSuccess) {                                                                 \
-      fprintf(stderr, "ries_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, \
-              __LINE__, cudaGetErrorString(e_));                                             \
-      abort();                                                                               \
-    }                                                                                        \
+/* A failed allocation is the caller's request being too deep for this GPU, not a fault: it unwinds as the
+   reference's out-of-memory exit (status 1, ries.c:4879) and ries_main() drops the engine so that the next call
+   starts from clean buffers.  Anything else is a genuine fault of the device or of this code. */
+inline void cuda_check_fail(cudaError_t e, const char* file, int line) {
+  if (e == cudaErrorMemoryAllocation) {
+    (void)cudaGetLastError();
+    fprintf(stderr, "ries_b200: out of device memory at %s:%d (search level too deep for this GPU)\n", file, line);
+    throw ExitRequest{1};
+  }
+  fprintf(stderr, "ries_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e), file, line, cudaGetErrorString(e));
+  abort();
+}
+#define CUDA_CHECK(x)                                          \
+  do {                                                         \
+    cudaError_t e_ = (x);                                      \
+    if (e_ != cudaSuccess) cuda_check_fail(e_, __FILE__, __LINE__); \
   } while (0)
 
 typedef unsigned long long u64;
@@ -84,6 +92,7 @@ struct DevBuf {
                                        reuse its physical memory for the bigger one */
       CUDA_CHECK(cudaFreeAsync(p, st));
       p = 0;
+      cap = 0;
     }
     CUDA_CHECK(cudaMallocAsync(&q, ncap * sizeof(T), st));
     if (zero) CUDA_CHECK(cudaMemsetAsync(q, 0, ncap * sizeof(T), st));
@@ -165,7 +174,7 @@ class DeviceEngine : public Engine {
     h_args_ = (PassArgs*)h_passin_;
     h_forms_ = (FormDesc*)(h_passin_ + PASSIN_FORMS_OFFSET);
     CUDA_CHECK(cudaMallocHost(&h_ptrs_, sizeof(DevPtrs)));
-    CUDA_CHECK(cudaMallocHost(&h_allctl_, 64 * sizeof(PassCtl)));
+    CUDA_CHECK(cudaMallocHost(&h_allctl_, RIES_MAX_RANKS * sizeof(PassCtl)));
     if (const char* e = getenv("RIES_SHARD_MIN")) shard_min_ = (u32)atol(e);
     memset(h_ptrs_, 0, sizeof(DevPtrs));
     for (int i = 0; i < 5; i++) CUDA_CHECK(cudaEventCreate(&ev_[i]));

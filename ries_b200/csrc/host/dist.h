@@ -13,6 +13,8 @@
 
 namespace ries {
 
+#define RIES_MAX_RANKS 64 /* the engine's pinned per-rank control blocks (engine.cu h_allctl_) */
+
 struct DistState {
   int rank = 0, world = 1;
   void* comm = 0;     /* ncclComm_t */

@@ -952,7 +952,8 @@ struct Search {
                      "  MAX_ELEN %d too small\n", lmax, rmax, RIES_MAX_ELEN);
           if (opt.NOS_options) out.printf("  too many symbols excluded via -N, -O or -S\n");
           if (opt.anagram) out.printf("  --numeric-anagram too restrictive\n");
-          out.printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n");
+          if (opt.derivative_margin == 0) /* ries.c:12504 */
+            out.printf("  target too big or small for k_vanished_dx (use --derivative-margin)\n");
           reported_exhaustion = true;
         }
         st.gen_total = lim_gentotal;
@@ -960,6 +961,13 @@ struct Search {
       if (opt.debug_y) {
         out.printf("gen_total %g (lhs %ld rhs %ld) searchmax %g gnm %ld\n", st.gen_total, st.lhs_insert,
                    st.rhs_insert, lim_gentotal, (long)num_matches);
+        /* bt_stats (ries.c:8399-8428, called at 12515): the node count is the table's row count.  The average
+           node depth describes the shape of the reference's unbalanced tree; the table here is a sorted array
+           and has no such shape -- a listed difference, except for the empty tree. */
+        out.printf("Current tree stats:\n");
+        out.printf("       Nodes: %ld\n", (long)resident_rows);
+        if (resident_rows == 0) out.printf("  Avg. Depth: -nan\n"); /* 0/0 on x86-64 */
+        else out.printf("  Avg. Depth: (not tracked: the value table is a sorted array)\n");
       }
       if (num_matches == 0) { /* 12522 */
         double tsec = now_sec() - t_start;
@@ -972,6 +980,8 @@ struct Search {
       if (st.gen_total >= lim_gentotal) going = false;
     }
 
+    if (opt.debug_y) /* ries.c:12550 */
+      out.printf("Level %.g search complete (gen_total exceeded lim_gentotal).\n", opt.levadj);
     if (reported_exhaustion) {
     } else if (num_matches == 0) {
       out.printf("No solution was found (try using -l%d", (int)floor(opt.levadj + 1.0));
