@@ -18,6 +18,7 @@ def pytest_configure(config):
 def normalise(text, prog=None):
     text = re.sub(r"Time: [0-9.]+", "Time: X", text)
     # -Dy traces (ries.c:12512-12530): elapsed seconds, and bt_stats' average tree depth (listed difference)
+    text = text.replace("\r", "\n")  # the goldens were captured in text mode (universal newlines)
     text = re.sub(r"and [0-9.]+ sec so far", "and X sec so far", text)
     text = re.sub(r"Avg\. Depth: (?!-nan).*", "Avg. Depth: N", text)
     if prog:

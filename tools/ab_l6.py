@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """A/B of kernel-tuning variants on the GPU box: for every _ab/*.so, a fresh process runs the full -l6 search
 (3 warm-ups + 5 timed), checks the report against the golden, and prints wall / per-stage device times.
-usage: tools/ab_l6.py            (driver)      tools/ab_l6.py --one <lib.so>   (worker)"""
+usage: tools/ab_l6.py [--env NAME:K=V,K=V ...]   (driver; every --env is one more run of the shipped library with
+those environment variables)      tools/ab_l6.py --one   (worker)"""
 import glob, os, re, shutil, subprocess, sys, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
@@ -29,9 +30,17 @@ if "--one" in sys.argv:
 else:
     lib = os.path.join(ROOT, "ries_b200", "libries_b200.so")
     shutil.copy(lib, lib + ".keep")
+    envs = []
+    for i, a in enumerate(sys.argv):
+        if a == "--env" and i + 1 < len(sys.argv):
+            name, _, kv = sys.argv[i + 1].partition(":")
+            envs.append((name, dict(x.split("=", 1) for x in kv.split(",") if x)))
     try:
         for v in [lib + ".keep"] + sorted(glob.glob(os.path.join(ROOT, "_ab", "*.so"))):
             shutil.copy(v, lib)
             subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=dict(os.environ, AB_NAME=os.path.basename(v)), timeout=300)
+        shutil.copy(lib + ".keep", lib)
+        for name, extra in envs:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=dict(os.environ, AB_NAME=name, **extra), timeout=300)
     finally:
         shutil.copy(lib + ".keep", lib); os.remove(lib + ".keep")
