@@ -31,7 +31,8 @@ struct EmulEngine : public ries::Engine {
   const char* name() const override { return "cpu-emulation"; }
   void begin(const RiesParams& p) override { P = p; table.clear(); }
 
-  long inserted_before(uint32_t seq, bool inclusive) override {
+  long inserted_before(const MatchEvent& ev, bool inclusive) override {
+    const uint32_t seq = ev.seq;
     long n = 0;
     for (uint32_t s : ins_seq) n += inclusive ? (s <= seq) : (s < seq);
     return n;

@@ -164,7 +164,8 @@ enum { OUT_NONE = 0, OUT_DEAD = 1, OUT_ERR = 2, OUT_LIVE = 3, OUT_DONE = 4 };
 /* A candidate the device hands back to the host replay (time order = (seq, kind)). */
 enum { EV_EXACT = 0, EV_PREV = 1, EV_NEXT = 2 };
 struct MatchEvent {
-  uint32_t seq;      /* insertion sequence number of the NEW expression inside its pass */
+  uint32_t seq;      /* tiny passes: insertion number of the NEW expression inside its pass; general passes: its
+                        form index (insertion order = (form, symbols), device/state.cuh SeqKey) */
   uint32_t kind;     /* EV_* ; replay order inside one seq is EXACT, PREV, NEXT */
   Row lhs;           /* as stored (before cv_simplify) */
   Row rhs;

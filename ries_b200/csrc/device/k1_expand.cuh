@@ -1,4 +1,6 @@
-// K1: enumerate + evaluate one expression position of every live prefix (ge_2 + exec).
+// K1 of the TINY passes: enumerate + evaluate one expression position of every live prefix (ge_2 + exec) inside
+// the single block of k_tiny_front (tiny_pass.cuh), children appended in the reference's insertion order.
+// The general kernel is k1_free.cuh.
 // Part of the single translation unit engine.cu (included inside namespace ries).
 #pragma once
 
@@ -27,57 +29,6 @@
 #endif
 #define IT_LIVE 0x4000u
 #define IT_DONE 0x8000u
-
-#define TS_AGG (1ull << 62)
-#define TS_INC (2ull << 62)
-#define TS_STATUS(x) ((x) >> 62)
-#define TS_LIVE(x) ((u32)(((x) >> 31) & 0x7fffffffull))
-#define TS_DONE(x) ((u32)((x)&0x7fffffffull))
-#define TS_PACK(st, live, done) ((st) | ((u64)(live) << 31) | (u64)(done))
-
-/* Decoupled look-back over tile aggregates (two counters packed in one word), in two steps so that a
-   block can publish a tile's aggregate, go on to the next tile, and only then resolve the first one's
-   exclusive prefix (by then its predecessors have long published). */
-__device__ __forceinline__ void tile_publish(volatile u64* state, u32 tile, u32 live_agg, u32 done_agg) {
-  __threadfence();
-  state[tile] = TS_PACK(tile == 0 ? TS_INC : TS_AGG, live_agg, done_agg);
-}
-
-/* Called by warp 0. */
-__device__ __forceinline__ void tile_lookback(volatile u64* state, u32 tile, u32 live_agg, u32 done_agg,
-                                              u32& live_excl, u32& done_excl) {
-  const u32 lane = threadIdx.x & 31;
-  live_excl = 0; done_excl = 0;
-  if (tile == 0) return;
-  u32 lsum = 0, dsum = 0;
-  int idx = (int)tile - 1;
-  while (true) {
-    int my = idx - (int)lane;
-    u64 w;
-    if (my >= 0) {
-      do { w = state[my]; } while (TS_STATUS(w) == 0);
-    } else {
-      w = TS_PACK(TS_INC, 0, 0);
-    }
-    u32 inc_mask = __ballot_sync(0xffffffffu, TS_STATUS(w) == 2);
-    /* lanes closer than the first inclusive one contribute their aggregates; that one its prefix */
-    u32 first_inc = inc_mask ? (u32)__ffs(inc_mask) - 1 : 32;
-    u32 lv = (lane <= first_inc) ? TS_LIVE(w) : 0;
-    u32 dv = (lane <= first_inc) ? TS_DONE(w) : 0;
-    for (int o = 16; o > 0; o >>= 1) {
-      lv += __shfl_xor_sync(0xffffffffu, lv, o);
-      dv += __shfl_xor_sync(0xffffffffu, dv, o);
-    }
-    lsum += lv; dsum += dv;
-    if (inc_mask) break;
-    idx -= 32;
-  }
-  if (lane == 0) {
-    __threadfence();
-    state[tile] = TS_PACK(TS_INC, lsum + live_agg, dsum + done_agg);
-  }
-  live_excl = lsum; done_excl = dsum;
-}
 
 /* Shared-memory state of one tile between its front half (phases 1-3) and its back half (phase 4). */
 struct TileBuf {
@@ -125,21 +76,6 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
     exp_sync<TINY>();
   }
   const DevPtrs D = *Dp;
-  if (!TINY) {
-    /* Programmatic dependent launch: the launches of one pass follow each other with the attribute set (see
-       enqueue_stage), so this kernel's blocks may start while the previous expression position is still
-       draining.  What does not depend on it -- the search constants -- is fetched first; then the next
-       position is allowed to start its own prologue, and only then do we wait for the previous one to be
-       complete and visible.  (Both instructions are no-ops in a launch without the attribute.) */
-    const u32* src = (const u32*)D.P;
-    u32* dst = (u32*)&P;
-    for (u32 i = tid; i < sizeof(RiesParams) / 4; i += EXP_THREADS) dst[i] = src[i];
-    const u32* tsrc = (const u32*)D.tt;
-    u32* tdst = (u32*)&TT;
-    for (u32 i = tid; i < sizeof(TestTables) / 4; i += EXP_THREADS) tdst[i] = tsrc[i];
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-  }
   const u32 lvl_begin = TINY ? s_lvl[0] : ctl->lvl_begin, lvl_end = TINY ? s_lvl[1] : ctl->lvl_end;
   const u32 n = lvl_end - lvl_begin;
   const u32 ntiles = (n + EXP_PARENTS - 1) / EXP_PARENTS;
@@ -161,18 +97,16 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
     const u32 lt = (1u << lane) - 1;
     Node* nodes = D.nodes;
     const FormDesc* forms = D.forms;
-    volatile u64* tile_state = (volatile u64*)D.tiles;
     u32 my_dead = 0;
     int cur = 0;
     bool have_prev = false;
     u32 tiny_tile = 0;
 
-    /* Tiles are handed out by ticket, so a tile's predecessors (which its look-back waits on) are always
-       held by blocks that are already running: safe even when not every block of the grid is resident
-       (several engines sharing the GPU on different streams).  The loop is software-pipelined: the front
-       half of tile t+1 runs between the publication of tile t's aggregate and t's look-back. */
+    /* The one block takes the tiles in order and keeps running sums of the children appended so far; a tile's
+       children are placed (phase 4) after the next tile's front half, as in the round-1 general kernel this
+       code comes from. */
     while (true) {
-      if (tid == 0) { if (!TINY) s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next = 0; }
+      if (tid == 0) s_next = 0;
       exp_sync<TINY>();
       const u32 tile = TINY ? tiny_tile++ : s_tile;
       const bool have_cur = tile < ntiles;
@@ -301,7 +235,6 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
           }
           if (tid == 0) {
             B.live_agg = la; B.done_agg = da;
-            if (!TINY) tile_publish(tile_state, tile, la, da);
           }
         }
       }
@@ -309,15 +242,9 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
       if (have_prev) {
         TileBuf& B = s_buf[cur ^ 1];
         const Staged* staged = D.staged + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * EXP_MAX_ITEMS;
-        if (TINY) {
-          if (tid == 0) {
-            s_live_base = s_run_live; s_done_base = s_run_done;
-            s_run_live += B.live_agg; s_run_done += B.done_agg;
-          }
-        } else if (warp == 0) {
-          u32 le, de;
-          tile_lookback(tile_state, B.tile, B.live_agg, B.done_agg, le, de);
-          if (lane == 0) { s_live_base = le; s_done_base = de; }
+        if (tid == 0) {
+          s_live_base = s_run_live; s_done_base = s_run_done;
+          s_run_live += B.live_agg; s_run_done += B.done_agg;
         }
         exp_sync<TINY>();
         const u32 T = B.total;
@@ -386,42 +313,6 @@ __device__ __forceinline__ void expand_level(const DevPtrs* __restrict__ Dp, con
     exp_sync<TINY>();
     return;
   }
-  /* ---- level finish by the last block to get here (replaces a separate launch) ---- */
-  exp_sync<TINY>();
-  if (tid == 0) {
-    __threadfence();
-    s_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
-  }
-  exp_sync<TINY>();
-  if (!s_last) return;
-  __threadfence();
-  volatile u64* tile_state = (volatile u64*)D.tiles;
-  const u64 last = ntiles ? tile_state[ntiles - 1] : 0;
-  exp_sync<TINY>();
-  for (u32 i = tid; i < ntiles; i += EXP_THREADS) tile_state[i] = 0;
-  if (tid == 0) {
-    u32 ovf = ctl->overflow;
-    if (!(ovf & (OVF_NODES | OVF_DONE))) {
-      u32 live = TS_LIVE(last), dn = TS_DONE(last);
-      u64 new_nodes = (u64)lvl_end + live;
-      u64 new_done = (u64)ctl->done_count + dn;
-      if (new_nodes > cap_nodes) ovf |= OVF_NODES;
-      if (new_done > cap_done) ovf |= OVF_DONE;
-      ctl->overflow = ovf;
-      ctl->lvl_begin = lvl_end;
-      /* on overflow stop expanding: the host grows the arenas and reruns the pass */
-      ctl->lvl_end = (ovf & (OVF_NODES | OVF_DONE)) ? lvl_end : (u32)new_nodes;
-      ctl->node_count = (new_nodes > 0xffffffffull) ? 0xffffffffu : (u32)new_nodes;
-      ctl->done_count = (new_done > 0xffffffffull) ? 0xffffffffu : (u32)new_done;
-    }
-    ctl->tile_ticket = 0;
-    ctl->blocks_done = 0;
-  }
-}
-
-__global__ void __launch_bounds__(EXP_THREADS, EXP_MIN_BLOCKS)
-k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
-  expand_level<false>(Dp, Ap, ctl);
 }
 
 /* fp64 FMA peak of this device, measured (denominator for K1's fp64 figure): 8 independent chains/thread */

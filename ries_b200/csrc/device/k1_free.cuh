@@ -1,0 +1,268 @@
+// K1, general kernel: enumerate + evaluate one expression position of every live prefix (ge_2 + exec).
+// Operator queues in shared memory, children written where they are produced -- no ordered append.
+// Part of the single translation unit engine.cu (included inside namespace ries).
+#pragma once
+
+/* Round 1's K1 emitted children in the reference's insertion order (decoupled look-back over tile aggregates plus
+   a placement phase per tile) and ran exec() on batches cut from ONE tile's (prefix, symbol) pairs.  ncu: 40 % of
+   the stall samples at block barriers (look-back wait, slowest warp of the exec phase), 24 of 32 lanes active.
+   A first order-free version of this kernel (profiles/r2_*) removed the look-back and showed what was under it:
+   a tile of 256 prefixes yields ~340 pairs over ~20 operators, i.e. batches of two or three operators each
+   (17 of 32 lanes active) hopping through 100 KB of exec() code (stall_no_instruction 44 %).  Hence:
+
+     ORDER-FREE  insertion order is a pure function of (form, symbols) (state.cuh, SeqKey): nothing downstream
+                 needs it materialised, so children go wherever there is room.
+     QUEUES      every block keeps one queue PER (complete?, SYMBOL) in shared memory, across tiles.  A round
+                 = phase P: thread = prefix of the next tile (taken by ticket): the integer symbol-append tests
+                   for ALL candidate symbols at once from host-built bit-mask tables (expand_mask;
+                   ries.c:9401-9445), every surviving pair appended to its symbol's queue;   -- block barrier
+                 phase C: only FULL batches of 32 are taken off the queues (the rest waits for the next tile),
+                   in queue order, so a batch is exactly one operator with 32 active lanes and neighbouring
+                   warps run the same code: exec() + value prunes (ries.c:5308-5950, 8962-9076) without
+                   divergence; the child -- a longer prefix or a complete expression -- is written straight to
+                   slot (round base + index in the round); thread 0 reserves the round's room with one atomic
+                   per output array while the first batches are already running.
+                 The last round of a block drains what is left.  A pair that fails leaves a HOLE (form =
+                 FORM_HOLE), skipped by whoever reads the slot next (~11 % of the slots at -l6).
+   Two barriers per round, no look-back, no staging of children, no partial batches but the last. */
+#ifndef XF_THREADS
+#define XF_THREADS 384 /* 2 blocks of 12 warps per SM (the queues of a block take 62 x 416 x 4 B at the default symbol set) */
+#endif
+#define XF_TILE XF_THREADS
+#ifndef XF_MIN_BLOCKS
+#define XF_MIN_BLOCKS 2
+#endif
+#define XF_CAP (XF_TILE + 32) /* a queue holds at most 31 left-overs + one tile's pairs of that symbol */
+#define XF_MAXQ (2 * RIES_MAX_SYMS)
+
+/* dynamic shared memory: nq queues of XF_CAP entries (u32: index of the prefix in the node arena) */
+__host__ __device__ inline size_t xf_dyn_smem(int nq) { return (size_t)nq * XF_CAP * sizeof(u32); }
+
+__global__ void __launch_bounds__(XF_THREADS, XF_MIN_BLOCKS)
+k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  u32* const s_ent = (u32*)s_dyn; /* [nq][XF_CAP] rings */
+  __shared__ RiesParams P;
+  __shared__ TestTables TT;
+  __shared__ u32 s_tail[XF_MAXQ];    /* entries ever appended to queue q */
+  __shared__ u32 s_head[2][XF_MAXQ]; /* entries ever taken off, by round parity (read-only during a round) */
+  __shared__ u32 s_cum[XF_MAXQ + 1]; /* this round: first batch of queue q in the round's batch list */
+  __shared__ u32 s_opcnt[RIES_MAX_SYMS];
+  __shared__ u32 s_tile, s_next[2], s_dead, s_gen, s_last;
+  __shared__ volatile u32 s_node_base, s_done_base;
+  __shared__ volatile u32 s_alloc_tag;
+  const u32 tid = threadIdx.x, lane = tid & 31;
+  const DevPtrs D = *Dp;
+  {
+    /* Programmatic dependent launch: the launches of one pass follow each other with the attribute set (see
+       enqueue_stage), so this kernel's blocks may start while the previous expression position is still
+       draining.  What does not depend on it -- the search constants -- is fetched first; then the next position
+       is allowed to start its own prologue, and only then do we wait for the previous one to be complete and
+       visible.  (Both instructions are no-ops in a launch without the attribute.) */
+    const u32* src = (const u32*)D.P;
+    u32* dst = (u32*)&P;
+    for (u32 i = tid; i < sizeof(RiesParams) / 4; i += XF_THREADS) dst[i] = src[i];
+    const u32* tsrc = (const u32*)D.tt;
+    u32* tdst = (u32*)&TT;
+    for (u32 i = tid; i < sizeof(TestTables) / 4; i += XF_THREADS) tdst[i] = tsrc[i];
+    if (tid == 0) { s_dead = 0; s_gen = 0; s_alloc_tag = 0; }
+    if (tid < RIES_MAX_SYMS) s_opcnt[tid] = 0;
+    if (tid < XF_MAXQ) { s_tail[tid] = 0; s_head[0][tid] = 0; s_head[1][tid] = 0; }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  __syncthreads();
+  const u32 lvl_begin = ctl->lvl_begin, lvl_end = ctl->lvl_end;
+  const u32 n = lvl_end - lvl_begin;
+  const u32 ntiles = (n + XF_TILE - 1) / XF_TILE;
+  const int using_x = Ap->using_x, cplx = Ap->cplx;
+  const u32 cap_nodes = Ap->cap_nodes, cap_done = Ap->cap_done;
+  /* queue of (complete, class, slot) = complete * nsq + qoff[class] + slot; symbol of queue q = sym_of_q */
+  const u32 qoff1 = (u32)P.cls_n[0], qoff2 = qoff1 + (u32)P.cls_n[1], nsq = qoff2 + (u32)P.cls_n[2];
+  const u32 nq = 2 * nsq;
+  if (ntiles != 0 && !(ctl->overflow & (OVF_NODES | OVF_DONE))) {
+    Node* nodes = D.nodes;
+    const FormDesc* __restrict__ forms = D.forms;
+    u32 my_dead = 0, my_gen = 0;
+    bool draining = false;
+    for (u32 par2 = 0; !draining; par2 ^= 1u) {
+      /* the batch cursor and the queue heads alternate between two copies: there is no barrier at the end of a
+         round, so a warp that is done may be here while another still pulls batches of the previous round; the
+         copy written here was last read two rounds ago, which every warp has left (it passed the barriers) */
+      if (tid == 0) { s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next[par2] = 0; }
+      __syncthreads(); /* also: every warp has left phase C of the previous round (queue entries may be overwritten) */
+      const u32 tile = s_tile;
+      draining = tile >= ntiles; /* no tile left for this block: one last round takes everything off the queues */
+      /* ---- phase P ---- */
+      if (!draining) {
+        const u32 p = lvl_begin + tile * XF_TILE + tid;
+        if (p < lvl_end) {
+          const Node par = nodes[p];
+          if (par.form != FORM_HOLE) {
+            const FormDesc& F = forms[par.form];
+            const int cls = F.cls[par.len];
+            const int ns = P.cls_n[cls];
+            const int atts = prefix_attrs(P, F, par, using_x);
+            u32 mask = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
+            my_dead += (u32)ns - (u32)__popc(mask);
+            const u32 q0 = ((par.len + 1 >= F.flen) ? nsq : 0u) + (cls == 0 ? 0u : cls == 1 ? qoff1 : qoff2);
+            while (mask) {
+              const u32 k = (u32)__ffs((int)mask) - 1;
+              mask &= mask - 1;
+              const u32 pos = atomicAdd(&s_tail[q0 + k], 1u);
+              s_ent[(q0 + k) * XF_CAP + pos % XF_CAP] = p;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      /* ---- the round's batch list: queue q contributes its full batches (everything when draining) ---- */
+      const u32* head = s_head[par2];
+      u32 nb_total, nb_live; /* batches of the round; of which from the queues of incomplete prefixes */
+      u32 T_live = 0;        /* slots the round needs in the node arena */
+      {
+        /* each lane looks after queues lane, lane + 32, lane + 64 */
+        u32 c[3], run = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const u32 q = (u32)j * 32 + lane;
+          const u32 avail = (q < nq) ? s_tail[q] - head[q] : 0;
+          c[j] = draining ? (avail + 31) >> 5 : avail >> 5;
+        }
+        /* exclusive scan in queue order: all of j = 0 first, then j = 1, then j = 2 */
+        u32 tot_live_b = 0, tot_live_s = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          u32 inc = c[j];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (u32)o) inc += v;
+          }
+          const u32 q = (u32)j * 32 + lane;
+          if (q <= nq && q < XF_MAXQ + 1) s_cum[q] = run + inc - c[j]; /* every warp writes the same values */
+          /* slots needed in the node arena: entries of the incomplete-prefix queues taken this round */
+          const u32 avail = (q < nq) ? s_tail[q] - head[q] : 0;
+          const u32 take = draining ? avail : (avail & ~31u);
+          u32 tl = (q < nsq) ? take : 0, bl = (q < nsq) ? c[j] : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            tl += __shfl_xor_sync(0xffffffffu, tl, o);
+            bl += __shfl_xor_sync(0xffffffffu, bl, o);
+          }
+          tot_live_s += tl; tot_live_b += bl;
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        nb_total = run; nb_live = tot_live_b; T_live = tot_live_s;
+        if (lane == 0 && nq >= 96) s_cum[96] = run; /* nq == XF_MAXQ: the sentinel is not any lane's queue */
+        __syncwarp();
+      }
+      /* room for every pair of the round: a live batch b owns node slots [32 b, 32 b + 32) of the round's range,
+         a done batch expression slots likewise; only the last batch of a queue can be partial (draining) */
+      const u32 slots_live = nb_live * 32u, slots_done = (nb_total - nb_live) * 32u;
+      (void)T_live;
+      if (tid == 0) {
+        const u32 nbase = slots_live ? atomicAdd(&ctl->node_count, slots_live) : 0;
+        const u32 dbase = slots_done ? atomicAdd(&ctl->done_count, slots_done) : 0;
+        u32 ovf = 0;
+        if ((u64)nbase + slots_live > cap_nodes) ovf |= OVF_NODES;
+        if ((u64)dbase + slots_done > cap_done) ovf |= OVF_DONE;
+        if (ovf) atomicOr(&ctl->overflow, ovf);
+        s_node_base = nbase; s_done_base = dbase;
+        __threadfence_block();
+        s_alloc_tag = (par2 << 30) + tile + 1;
+      }
+      if (tid < XF_MAXQ) { /* next round's heads */
+        const u32 q = tid;
+        const u32 avail = (q < nq) ? s_tail[q] - head[q] : 0;
+        s_head[par2 ^ 1][q] = head[q] + (draining ? avail : (avail & ~31u));
+      }
+      /* ---- phase C ---- */
+      while (true) {
+        u32 b = 0;
+        if (lane == 0) b = atomicAdd(&s_next[par2], 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= nb_total) break;
+        /* from the END of the list: the queues are in slot order and the heavy operators of a class (^ v L A, the
+           trigonometric functions) are its last slots, so they start first and the constants fill the tail */
+        b = nb_total - 1u - b;
+        /* queue of batch b: the last q with s_cum[q] <= b (s_cum is non-decreasing, s_cum[nq] = nb_total) */
+        u32 q = 0;
+#pragma unroll
+        for (int s = 64; s > 0; s >>= 1)
+          if (q + s < nq && s_cum[q + s] <= b) q += s;
+        const u32 j0 = (b - s_cum[q]) * 32u + lane;      /* index in the queue, from its head */
+        const u32 avail = s_tail[q] - head[q];
+        const bool act = j0 < avail;
+        const bool complete = q >= nsq;
+        const u32 qs = complete ? q - nsq : q;
+        const int cls = qs < qoff1 ? 0 : qs < qoff2 ? 1 : 2;
+        const u32 k = qs - (cls == 0 ? 0u : cls == 1 ? qoff1 : qoff2);
+        const int g = P.trial[cls][k];
+        if (lane == 0) atomicAdd(&s_opcnt[g], min(32u, avail - (b - s_cum[q]) * 32u)); /* exec() calls per symbol */
+        int oc = OUT_NONE;
+        Node child;
+        Node par;
+        if (act) {
+          const u32 p = s_ent[q * XF_CAP + (head[q] + j0) % XF_CAP];
+          par = nodes[p];
+          oc = expand_exec(P, cls, g, complete, nodes, par, p, using_x, child);
+          if (oc == OUT_DEAD) my_dead++;
+        }
+        while (s_alloc_tag != (par2 << 30) + tile + 1) {} /* set long ago, as a rule */
+        if (!complete) {
+          const u32 pos = s_node_base + b * 32u + lane;
+          if (pos < cap_nodes) {
+            if (oc == OUT_LIVE) {
+              expand_finish(P, par, g, child);
+              nodes[pos] = child;
+            } else { /* hole (failed pair, or the tail of a partial batch): only the word that holds the form */
+              ((uint4*)(nodes + pos))[2] = make_uint4(RIES_NO_NODE, FORM_HOLE, 0u, 0u);
+            }
+          }
+        } else {
+          const u32 pos = s_done_base + (b - nb_live) * 32u + lane;
+          if (pos < cap_done) {
+            if (oc == OUT_DONE) {
+              expand_finish(P, par, g, child);
+              Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
+              D.done[pos] = r;
+              D.done_form[pos] = child.form;
+            } else {
+              D.done_form[pos] = (uint16_t)FORM_HOLE;
+            }
+          }
+          if (oc == OUT_DONE) my_gen++;
+        }
+      }
+    }
+    /* block-level counters -> one atomic each per block */
+    for (int o = 16; o > 0; o >>= 1) {
+      my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
+      my_gen += __shfl_xor_sync(0xffffffffu, my_gen, o);
+    }
+    if (lane == 0) { if (my_dead) atomicAdd(&s_dead, my_dead); if (my_gen) atomicAdd(&s_gen, my_gen); }
+    __syncthreads();
+    if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
+    if (tid == 0 && s_gen) atomicAdd(&ctl->gen, (u64)s_gen);
+    if (tid < RIES_MAX_SYMS && s_opcnt[tid]) atomicAdd(&D.opcnt[(using_x ? RIES_MAX_SYMS : 0) + tid], (u64)s_opcnt[tid]);
+  }
+  /* ---- level finish by the last block to get here (replaces a separate launch) ---- */
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) {
+    __threadfence();
+    const u32 ovf = *(volatile u32*)&ctl->overflow;
+    const u32 alloc = *(volatile u32*)&ctl->node_count;
+    ctl->lvl_begin = lvl_end;
+    /* on overflow stop expanding: the host grows the arenas and reruns the pass */
+    ctl->lvl_end = (ovf & (OVF_NODES | OVF_DONE)) ? lvl_end : alloc;
+    ctl->tile_ticket = 0;
+    ctl->blocks_done = 0;
+  }
+}

@@ -1,103 +1,105 @@
-// Regroup into insertion order + K2: stable onesweep LSD radix sort on the fp64 value.
+// Sort keys + pre-dedupe, and K2: onesweep LSD radix sort on the fp64 value.
 // Part of the single translation unit engine.cu (included inside namespace ries).
 #pragma once
 
-/* ------------------------------------------------ survivors into insertion (DFS) order --- */
-/* Within one level the completed expressions are ordered (form, lexicographic) and every form
-   completes at exactly one level, so a form's expressions are contiguous in done[]. */
+/* ------------------------------------------------ sort keys + pre-dedupe ------------------- */
 __device__ __forceinline__ bool pass_ok(const PassCtl* C) { return (C->overflow & (OVF_NODES | OVF_DONE)) == 0; }
-
-__global__ void k_form_bounds(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
-  stage_stamp(C, 1);
-  if (!pass_ok(C)) return;
-  const u32 n = C->done_count;
-  const uint16_t* done_form = A->gathered ? Dp->gdone_form : Dp->done_form;
-  u32* form_first = Dp->form_first;
-  u32* form_cnt = Dp->form_cnt;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint16_t f = done_form[i];
-    if (i == 0 || done_form[i - 1] != f) form_first[f] = i;
-    if (i + 1 == n || done_form[i + 1] != f) form_cnt[f] = i + 1; /* end; fixed up in k_form_scan */
-  }
-}
-
-__global__ void k_form_scan(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
-  /* single block: the number of forms is at most a few thousand */
-  __shared__ u32 s_carry;
-  __shared__ u32 s_tmp[1024];
-  if (!pass_ok(C) || C->done_count == 0) return;
-  const u32 nforms = (u32)A->nforms;
-  const u32* form_first = Dp->form_first;
-  u32* form_cnt = Dp->form_cnt;
-  u32* form_base = Dp->form_base;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (u32 base = 0; base < nforms; base += 1024) {
-    u32 f = base + threadIdx.x;
-    u32 c = 0;
-    if (f < nforms) {
-      u32 e = form_cnt[f];
-      c = e ? (e - form_first[f]) : 0;
-    }
-    s_tmp[threadIdx.x] = c;
-    __syncthreads();
-    for (u32 o = 1; o < 1024; o <<= 1) {
-      u32 v = (threadIdx.x >= o) ? s_tmp[threadIdx.x - o] : 0;
-      __syncthreads();
-      s_tmp[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (f < nforms) form_base[f] = s_carry + s_tmp[threadIdx.x] - c;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry += s_tmp[1023];
-    __syncthreads();
-  }
-}
 
 __device__ __forceinline__ u64 key_of(double v) { /* order-preserving map double -> u64 */
   u64 b = (u64)__double_as_longlong(v);
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
-/* Survivors into insertion order, their sort keys, and (fused, so the keys are not read again) the
-   histograms of all eight key digits for the radix sort below. */
-__global__ void __launch_bounds__(256)
-k_reorder(const DevPtrs* Dp, const PassArgs* A, const PassCtl* C) {
+/* Every filled slot of done[] gets its sort key -- unless the value is already in the table ON THE SAME SIDE:
+   bt_insert finds the equal node and check_exact_match returns at once for a same-side pair (ries.c:8648-8661,
+   8550-8593), so such an expression changes nothing but the "expressions" counter, which K1 has already
+   counted.  At -l6 that is 70-84 % of what the big passes generate, found here with ONE 32-byte probe of the
+   side's hash set instead of eight digit passes and a table search.  The survivors are compacted (block
+   aggregate, one atomic per 1024 slots; their order is free: insertion order is recovered from (form, symbols)
+   wherever it matters) together with the histograms of all eight key digits for the radix sort below.
+   Sharded passes: keep[] is cleared for every slot (k_local_filter sets the winners). */
+#define KK_THREADS 256
+#define KK_ITEMS 4
+#define KK_CHUNK (KK_THREADS * KK_ITEMS)
+__global__ void __launch_bounds__(KK_THREADS)
+k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
   __shared__ u32 s_h[8][256];
+  __shared__ u32 s_cnt[KK_ITEMS * (KK_THREADS / 32)];
+  __shared__ u32 s_base;
+  stage_stamp(C, 1);
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
-  if (blockIdx.x * blockDim.x >= n) return;
-  const DevPtrs D = *Dp;
+  if ((u64)blockIdx.x * KK_CHUNK >= n) return;
+  const DevPtrs& D = *Dp;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Row* __restrict__ done = A->gathered ? D.gdone : D.done;
   const uint16_t* __restrict__ done_form = A->gathered ? D.gdone_form : D.done_form;
-  for (int d = 0; d < 8; d++) s_h[d][threadIdx.x] = 0;
+  const int side = A->using_x ? 1 : 0;
+  const u64* __restrict__ hs = Dp->hset[side];
+  const u32 hlog = Dp->hset_log2[side];
+  const bool clear_keep = A->shard_world > 1 && !A->gathered;
+  u64* keys = D.keys[0];
+  u32* idx = D.idx[0];
+  for (int d = 0; d < 8; d++) s_h[d][tid] = 0;
   __syncthreads();
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint16_t f = done_form[i];
-    u32 pos = D.form_base[f] + (i - D.form_first[f]);
-    Row r = done[i];
-    D.surv[pos] = r;
-    D.surv_form[pos] = f;
-    const u64 k = key_of(r.val);
-    D.keys[0][pos] = k;
-    D.idx[0][pos] = pos;
+  for (u32 base = blockIdx.x * KK_CHUNK; base < n; base += gridDim.x * KK_CHUNK) {
+    u64 k[KK_ITEMS];
+    u32 flags = 0;
 #pragma unroll
-    for (int d = 0; d < 8; d++) atomicAdd(&s_h[d][(u32)(k >> (8 * d)) & 255u], 1u);
+    for (int r = 0; r < KK_ITEMS; r++) {
+      const u32 i = base + r * KK_THREADS + tid;
+      bool keep = false;
+      k[r] = 0;
+      if (i < n) {
+        if (clear_keep) D.keep[i] = 0;
+        if (done_form[i] != FORM_HOLE) {
+          k[r] = key_of(done[i].val);
+          keep = !hset_contains(hs, hlog, k[r]);
+        }
+      }
+      const u32 b = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_cnt[r * (KK_THREADS / 32) + warp] = __popc(b);
+      if (keep) flags |= (1u << r) | (__popc(b & ((1u << lane) - 1)) << (8 + 6 * r)); /* rank in the warp: 5 bits used of 6 */
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const u32 c = s_cnt[lane];
+      u32 inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += v;
+      }
+      s_cnt[lane] = inc - c;
+      if (lane == 31) s_base = inc ? atomicAdd(&C->n_keys, inc) : 0;
+    }
+    __syncthreads();
+    const u32 cbase = s_base;
+#pragma unroll
+    for (int r = 0; r < KK_ITEMS; r++) {
+      if ((flags >> r) & 1u) {
+        const u32 pos = cbase + s_cnt[r * (KK_THREADS / 32) + warp] + ((flags >> (8 + 6 * r)) & 63u);
+        keys[pos] = k[r];
+        idx[pos] = base + r * KK_THREADS + tid;
+#pragma unroll
+        for (int d = 0; d < 8; d++) atomicAdd(&s_h[d][(u32)(k[r] >> (8 * d)) & 255u], 1u);
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   SortCtl* ctl = D.sortctl;
   for (int d = 0; d < 8; d++) {
-    u32 c = s_h[d][threadIdx.x];
-    if (c) atomicAdd(&ctl->ghist[d][threadIdx.x], c);
+    u32 c = s_h[d][tid];
+    if (c) atomicAdd(&ctl->ghist[d][tid], c);
   }
 }
 
 /* ---------------------------------------------------------------- K2: radix sort --------- */
 /* Stable LSD radix sort of (u64 key, u32 payload), 8 digits of 8 bits, "onesweep" style: the histograms
-   of all eight digits come from k_reorder (which writes the keys); each digit pass is then a single
-   kernel in which every 4096-key chunk gets its per-digit output offsets by decoupled look-back over the
-   chunks before it (chunks are taken in ticket order, so equal keys keep their input order = insertion
-   order). */
+   of all eight digits come from k_keys (which writes the keys); each digit pass is then a single kernel in
+   which every 4096-key chunk gets its per-digit output offsets by decoupled look-back over the chunks before
+   it (chunks are taken in ticket order, so the sort is stable -- which nothing relies on any more: equal
+   values are ranked by their insertion-order keys in k_classify_compact). */
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)
 #ifndef RS_ITEMS
@@ -129,7 +131,7 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
   __shared__ u32 s_wtot[RS_WARPS];
   __shared__ u32 s_chunk;
   if (!pass_ok(C)) return;
-  const u32 n = C->done_count;
+  const u32 n = C->n_keys;
   const u32 nchunks = (n + RS_CHUNK - 1) / RS_CHUNK;
   if (blockIdx.x >= nchunks) return;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -51,10 +51,12 @@ __device__ __forceinline__ u32 warp_lower_bound(const double* __restrict__ a, u3
   return lo + __popc(__ballot_sync(0xffffffffu, lt));
 }
 
-/* For every survivor in sorted order: is it a new distinct value?  New rows are compacted (ticketed
-   chunks + look-back keep them in value order) together with their gap = lower bound in the old
-   table.  Duplicates of an opposite-side table row become EXACT events (check_exact_match's side
-   test, ries.c:8550-8593).
+/* For every sorted key: is it a new distinct value?  Of a run of equal new values the row the tree would have
+   kept is the one inserted first (bt_insert, ries.c:8648-8661): the first element of the run walks the run and
+   picks the smallest insertion-order key (SeqKey; runs of NEW values are short -- what the table already holds
+   on this side never got here).  New rows are compacted (ticketed chunks + look-back keep them in value
+   order) together with their gap = lower bound in the old table.  Duplicates of an opposite-side table row
+   become EXACT events (check_exact_match's side test, ries.c:8550-8593).
    The survivors of a chunk are consecutive in value order, so their lower bounds all fall between the
    lower bounds of the chunk's first and last value: two warp searches find that window, the window of
    table keys is staged in shared memory with coalesced loads, and the per-survivor searches run there.
@@ -70,17 +72,18 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   __shared__ u32 s_chunk, s_base, s_lo, s_hi;
   stage_stamp(C, 2);
   if (!pass_ok(C)) return;
-  const u32 n = C->done_count;
+  const u32 n = C->n_keys;
   const u32 nchunks = (n + CC_CHUNK - 1) / CC_CHUNK;
   if (blockIdx.x >= nchunks) return;
-  const DevPtrs D = *Dp;
+  const DevPtrs& D = *Dp;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 cur = T->cur, nt = T->nt;
   const double* __restrict__ tval = D.tval[cur];
   const Row* __restrict__ trow = D.trow[cur];
   const u64* __restrict__ keys = D.keys[0]; /* 8 digit passes: the sorted order ends in buffer 0 */
   const u32* __restrict__ idx = D.idx[0];
-  const Row* __restrict__ surv = D.surv;
+  const Row* __restrict__ surv = A->gathered ? D.gdone : D.done;
+  const uint16_t* __restrict__ surv_form = A->gathered ? D.gdone_form : D.done_form;
   const int using_x = A->using_x, skip_exact = A->skip_exact;
   volatile u64* state = (volatile u64*)D.cc_state;
   const u64 epoch = (u64)(T->epoch + 8u);
@@ -103,11 +106,13 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
     const u32 lo = s_lo, hi = s_hi;        /* every lower bound of the chunk is in [lo, hi] */
     const u32 wn = hi - lo;                 /* keys that take part in the searches */
     const u32 wload = min(hi + 1, nt) - lo; /* + the one at `hi`, for the equality test */
-    const bool in_smem = wn <= CC_WIN;
-    if (in_smem)
-      for (u32 j = tid; j < wload; j += CC_THREADS) s_win[j] = tval[lo + j];
+    /* the window goes to shared memory -- every S-th key of it when it is longer than the buffer (after the
+       pre-dedupe the keys of a chunk are spread over a wider stretch of the table than they used to be): the
+       search runs over the samples there and finishes among the S keys between two samples in global memory */
+    const u32 S = (wload + CC_WIN - 1) / CC_WIN > 1 ? (wload + CC_WIN - 1) / CC_WIN : 1;
+    const u32 ns = (wload + S - 1) / S;
+    for (u32 j = tid; j < ns; j += CC_THREADS) s_win[j] = tval[lo + j * S];
     __syncthreads();
-    const double* win = in_smem ? s_win : tval + lo;
     u32 pos[CC_ITEMS], sq[CC_ITEMS];
     u32 flags = 0;
 #pragma unroll
@@ -121,26 +126,50 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
         const u32 s = idx[i];
         sq[r] = s;
         const bool dup_prev = (i > 0) && (keys[i - 1] == k);
-        u32 a = 0, b = wn;
+        u32 a = 0, b = (S == 1) ? wn : ns;
         while (a < b) {
           u32 mid = (a + b) >> 1;
-          if (win[mid] < v) a = mid + 1; else b = mid;
+          if (s_win[mid] < v) a = mid + 1; else b = mid;
+        }
+        bool in_table;
+        if (S == 1) {
+          in_table = (lo + a < nt) && (s_win[a] == v);
+        } else { /* sample a is the first one >= v: the lower bound lies in ((a-1) S, a S] */
+          u32 l2 = a ? (a - 1) * S + 1 : 0, h2 = min(a * S, wn);
+          while (l2 < h2) {
+            u32 mid = (l2 + h2) >> 1;
+            if (tval[lo + mid] < v) l2 = mid + 1; else h2 = mid;
+          }
+          a = l2;
+          in_table = (lo + a < nt) && (tval[lo + a] == v);
         }
         const u32 p = lo + a;
         pos[r] = p;
-        const bool in_table = (p < nt) && (win[a] == v);
         if (in_table) {
           if (!skip_exact) {
             Row t = trow[p];
             bool tree_is_lhs = (t.der != 0.0);
             if (using_x ? !tree_is_lhs : tree_is_lhs) {
               Row f = surv[s];
-              if (using_x) push_event(D.events, A->cap_events, C, s, EV_EXACT, f, t);
-              else push_event(D.events, A->cap_events, C, s, EV_EXACT, t, f);
+              if (using_x) push_event(D.events, A->cap_events, C, surv_form[s], EV_EXACT, f, t);
+              else push_event(D.events, A->cap_events, C, surv_form[s], EV_EXACT, t, f);
             }
           }
         } else if (!dup_prev) {
           fl = true;
+          /* the run of this value: the expression inserted first wins */
+          if (i + 1 < n && keys[i + 1] == k) {
+            u32 w = s;
+            Sym128 ws = surv[w].sym;
+            u32 wf = surv_form[w];
+            for (u32 j = i + 1; j < n && keys[j] == k; j++) {
+              const u32 s2 = idx[j];
+              const Sym128 s2s = surv[s2].sym;
+              const u32 s2f = surv_form[s2];
+              if (seq_before(s2f, s2s, wf, ws)) { w = s2; ws = s2s; wf = s2f; }
+            }
+            sq[r] = w;
+          }
         }
       }
       const u32 b = __ballot_sync(0xffffffffu, fl);
@@ -192,6 +221,10 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
         const u32 u = cbase + s_cnt[r * (CC_THREADS / 32) + warp] + __popc(b & ((1u << lane) - 1));
         D.uniq_seq[u] = sq[r];
         D.uniq_gap[u] = pos[r];
+        SeqKey sk;
+        const Sym128 sy = surv[sq[r]].sym;
+        sk.lo = sy.lo; sk.hi = sy.hi; sk.form = surv_form[sq[r]]; sk.pad = 0;
+        D.uniq_sk[u] = sk;
       }
     }
     __syncthreads();
@@ -199,34 +232,44 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
 }
 
 /* K3 + merge of the new rows.  A new row's predecessor AT ITS INSERTION TIME is the old-table row below
-   its gap unless a same-pass row with a smaller sequence number already sits between them (that one is
-   same-side, so no test happens: check_sides, ries.c:8496-8538).  Likewise for the successor.  The row is
-   read once: it goes to its place in the merged table and into the neighbour tests. */
+   its gap unless a same-pass row inserted earlier already sits between them (that one is same-side, so no test
+   happens: check_sides, ries.c:8496-8538).  Likewise for the successor.  "Inserted earlier" = smaller
+   insertion-order key (uniq_sk).  The row is read once: it goes to its place in the merged table, its key
+   into the side's hash set, and into the neighbour tests. */
 __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
   if (!pass_ok(C)) return;
   const u32 nu = C->n_uniq;
-  const DevPtrs D = *Dp;
+  const DevPtrs& D = *Dp;
   const u32 nt = T->nt;
   const Row* __restrict__ trow = D.trow[T->cur];
   Row* mrow = D.trow[T->cur ^ 1];
   double* mval = D.tval[T->cur ^ 1];
   const u32* __restrict__ uniq_seq = D.uniq_seq;
   const u32* __restrict__ uniq_gap = D.uniq_gap;
+  const SeqKey* __restrict__ uniq_sk = D.uniq_sk;
+  const Row* __restrict__ surv = A->gathered ? D.gdone : D.done;
   const int using_x = A->using_x;
   const double best_match0 = A->best_match0;
+  u64* hs = Dp->hset[using_x ? 1 : 0];
+  const u32 hlog = Dp->hset_log2[using_x ? 1 : 0];
   for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
-    const u32 s = uniq_seq[u], g = uniq_gap[u];
-    const Row f = D.surv[s];
+    const u32 g = uniq_gap[u];
+    const Row f = surv[uniq_seq[u]];
     mrow[u + g] = f;
     mval[u + g] = f.val;
+    hset_insert(hs, hlog, key_of(f.val));
     bool test_prev = g > 0, test_next = g < nt;
-    if (test_prev) {
-      for (u32 j = u; j-- > 0 && uniq_gap[j] == g;)
-        if (uniq_seq[j] < s) { test_prev = false; break; }
-    }
-    if (test_next) {
-      for (u32 j = u + 1; j < nu && uniq_gap[j] == g; j++)
-        if (uniq_seq[j] < s) { test_next = false; break; }
+    const bool nb_prev = u > 0 && uniq_gap[u - 1] == g, nb_next = u + 1 < nu && uniq_gap[u + 1] == g;
+    if ((test_prev && nb_prev) || (test_next && nb_next)) {
+      const SeqKey me = uniq_sk[u];
+      if (test_prev && nb_prev) {
+        for (u32 j = u; j-- > 0 && uniq_gap[j] == g;)
+          if (seq_before(uniq_sk[j], me)) { test_prev = false; break; }
+      }
+      if (test_next && nb_next) {
+        for (u32 j = u + 1; j < nu && uniq_gap[j] == g; j++)
+          if (seq_before(uniq_sk[j], me)) { test_next = false; break; }
+      }
     }
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !test_prev : !test_next) continue;
@@ -238,7 +281,7 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
       double total = L.der - R.der;
       double score = fabs((R.val - L.val) / total);
       if (score > best_match0) continue; /* NaN passes, as in the reference's test (8270) */
-      push_event(D.events, A->cap_events, C, s, side == 0 ? EV_PREV : EV_NEXT, L, R);
+      push_event(D.events, A->cap_events, C, uniq_sk[u].form, side == 0 ? EV_PREV : EV_NEXT, L, R);
     }
   }
 }

@@ -34,7 +34,7 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
   const u32 nu = C->n_uniq;
   if (nu == 0) return; /* nothing inserted: the live buffer stays as it is */
   const u32 nt = T->nt;
-  const DevPtrs D = *Dp;
+  const DevPtrs& D = *Dp;
   const Row* __restrict__ trow = D.trow[T->cur];
   Row* mrow = D.trow[T->cur ^ 1];
   double* mval = D.tval[T->cur ^ 1];
@@ -77,5 +77,18 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
       }
     }
     __syncthreads();
+  }
+}
+
+/* A side's hash set re-entered from the table (after the set has grown, or after a pass whose merge was undone). */
+__global__ void k_hset_rebuild(const DevPtrs* Dp, const TableState* T, int side) {
+  const DevPtrs& D = *Dp;
+  const u32 nt = T->nt;
+  const Row* __restrict__ trow = D.trow[T->cur];
+  u64* hs = Dp->hset[side];
+  const u32 hlog = Dp->hset_log2[side];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+    const Row r = trow[i];
+    if (((r.der != 0.0) ? 1 : 0) == side) hset_insert(hs, hlog, key_of(r.val));
   }
 }

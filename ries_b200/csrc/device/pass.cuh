@@ -15,16 +15,12 @@ __device__ __forceinline__ void pass_begin_body(const DevPtrs* D, const PassArgs
     r.pad0 = 0; r.pad1 = 0;
     D->nodes[j] = r;
   }
-  for (u32 i = threadIdx.x; i < nforms; i += blockDim.x) {
-    D->form_first[i] = 0;
-    D->form_cnt[i] = 0;
-  }
   u32* sc = (u32*)D->sortctl;
   for (u32 i = threadIdx.x; i < sizeof(SortCtl) / 4; i += blockDim.x) sc[i] = 0;
   if (threadIdx.x == 0) {
     C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
     C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
-    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0;
+    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0; C->n_keys = 0; C->gen = 0;
     C->stamp[1] = C->stamp[2] = C->stamp[3] = C->stamp[4] = 0;
     u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
     if (e == 0) e = 16;

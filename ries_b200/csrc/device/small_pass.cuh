@@ -1,4 +1,4 @@
-// Small passes: regroup + sort + classify + match + merge-new in one block.
+// Tiny passes: regroup + sort + classify + match + merge-new in one block (called by k_tiny_front).
 // Part of the single translation unit engine.cu (included inside namespace ries).
 #pragma once
 
@@ -248,6 +248,7 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
     const Row f = D.surv[sidx];
     mrow[u + g] = f;
     mval[u + g] = f.val;
+    hset_insert(Dp->hset[using_x ? 1 : 0], Dp->hset_log2[using_x ? 1 : 0], key_of(f.val)); /* later passes' pre-dedupe */
     bool test_prev = g > 0, test_next = g < nt;
     if (test_prev) {
       for (u32 j = u; j-- > 0 && s_ugap[j] == g;)
@@ -272,10 +273,3 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
   }
 }
 
-__global__ void __launch_bounds__(SP_THREADS, 1)
-k_small_post(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
-  stage_stamp(C, 1);
-  small_post_body(Dp, A, C, T);
-  __syncthreads();
-  stage_stamp(C, 2); /* k_merge_old is all there is to stage 2 after this kernel */
-}

@@ -41,10 +41,11 @@ struct PassCtl {
   u32 overflow;
   u32 chunk_ticket;       /* k_classify_compact */
   u32 nt_before;          /* table rows before this pass */
-  u32 pad;
+  u32 n_keys;             /* complete expressions that survive the pre-dedupe and go through the sort */
   u64 dead;               /* dead-ends of the pass */
   u32 aux_ticket;         /* k_local_filter / k_compact_kept (sharded passes) */
   u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
+  u64 gen;                /* complete expressions generated (g_ne, ries.c:9190): done_count counts SLOTS, holes included */
   /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] regroup +
      sort, [2] classify/match/merge, [3] refine, [4] end.  Written by thread 0 of block 0 of the stage's first
      kernel (the kernels of a pass run back to back on one stream), read by the host from the copied-back
@@ -81,6 +82,70 @@ struct TableState {
   u32 pad;
 };
 
+/* INSERTION ORDER WITHOUT ORDERED OUTPUT.  The reference inserts expressions one at a time, and what it prints
+   depends on the order: forms in pre-order, within a form the lexicographic order of symbol TRIAL positions
+   (ge_2's loop, ries.c:9388).  Trial order within a class is the order of the symbol table (setup.cc fills
+   trial[] by ascending table index), so for two expressions of one pass
+        a was inserted before b   <=>   (form_a, code_a[0], code_a[1], ...) < (form_b, code_b[0], ...)
+   lexicographically, the codes being the 6-bit table indices stored in Sym128.  K1 therefore does not have to
+   EMIT expressions in insertion order (which took a look-back chain over all tiles in flight and a second phase
+   per tile): every consumer that needs "who came first" compares these keys. */
+struct SeqKey {
+  u64 lo, hi; /* Sym128 of the expression as enumerated */
+  u32 form, pad;
+};
+
+__device__ __forceinline__ bool sym_before(u64 alo, u64 ahi, u64 blo, u64 bhi) {
+  /* position 0 sits in the lowest 6 bits: the first differing position is the lowest differing bit's group */
+  const u64 xl = alo ^ blo;
+  if (xl) {
+    const int g = (__ffsll((long long)xl) - 1) / 6;
+    if (g < 10) return ((alo >> (6 * g)) & 63ull) < ((blo >> (6 * g)) & 63ull);
+    /* position 10 straddles the two words (bits 60..65) */
+    return (((alo >> 60) | (ahi << 4)) & 63ull) < (((blo >> 60) | (bhi << 4)) & 63ull);
+  }
+  const u64 xh = ahi ^ bhi;
+  if (!xh) return false;
+  const int t = __ffsll((long long)xh) - 1; /* bit t of hi is bit 64 + t of the whole */
+  if (t < 2) return (((alo >> 60) | (ahi << 4)) & 63ull) < (((blo >> 60) | (bhi << 4)) & 63ull); /* equal low words: decided by the two high bits of position 10 */
+  const int g = (t - 2) / 6; /* position 11 + g */
+  return ((ahi >> (2 + 6 * g)) & 63ull) < ((bhi >> (2 + 6 * g)) & 63ull);
+}
+__device__ __forceinline__ bool seq_before(u32 fa, const Sym128& a, u32 fb, const Sym128& b) {
+  if (fa != fb) return fa < fb;
+  return sym_before(a.lo, a.hi, b.lo, b.hi);
+}
+__device__ __forceinline__ bool seq_before(const SeqKey& a, const SeqKey& b) {
+  if (a.form != b.form) return a.form < b.form;
+  return sym_before(a.lo, a.hi, b.lo, b.hi);
+}
+
+#define FORM_HOLE 0xffffu /* done_form[] / Node::form of a slot that was allocated but not filled */
+
+/* Hash set of table keys, one per side: 4-slot buckets of 32 bytes (one DRAM sector per probe).  It only has to be
+   SOUND: a key it reports is in the table on that side.  A key that found its bucket full is simply not
+   remembered (the sort and the table search after it are the arbiter), so there is no overflow handling. */
+__device__ __forceinline__ u64 hset_bucket(u64 key, u32 log2b) { return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2b); }
+__device__ __forceinline__ bool hset_contains(const u64* __restrict__ slots, u32 log2b, u64 key) {
+  if (!key) return false;
+  const ulonglong2* b = (const ulonglong2*)(slots + (hset_bucket(key, log2b) << 2));
+  const ulonglong2 a = b[0], c = b[1];
+  return a.x == key || a.y == key || c.x == key || c.y == key;
+}
+__device__ __forceinline__ void hset_insert(u64* slots, u32 log2b, u64 key) {
+  if (!key) return;
+  unsigned long long* b = (unsigned long long*)(slots + (hset_bucket(key, log2b) << 2));
+  /* one look at the bucket (a single 32-byte sector), then one compare-and-swap on the first free slot: a CAS per
+     slot in turn costs a DRAM round trip each, and this is the hot spot of the merge kernel */
+  const ulonglong2 a = __ldcg((const ulonglong2*)b), c = __ldcg((const ulonglong2*)b + 1);
+  if (a.x == key || a.y == key || c.x == key || c.y == key) return;
+  int s = !a.x ? 0 : !a.y ? 1 : !c.x ? 2 : !c.y ? 3 : 4;
+  for (; s < 4; s++) {
+    const unsigned long long old = atomicCAS(b + s, 0ull, (unsigned long long)key);
+    if (old == 0ull || old == key) return;
+  }
+}
+
 /* Every buffer the kernels touch.  Lives in device memory; the host rewrites it when a buffer grows,
    so kernel arguments (and the captured graphs) never change. */
 struct DevPtrs {
@@ -92,23 +157,21 @@ struct DevPtrs {
   uint16_t* done_form;
   Row* gdone;           /* all ranks' complete expressions, rank-major (sharded passes only) */
   uint16_t* gdone_form;
-  Row* surv;
-  uint16_t* surv_form; /* form index of surv[i] (sharded passes: needed again after the exchange) */
-  unsigned char* keep; /* sharded passes: surv[i] takes part in the exchange */
+  Row* surv;           /* tiny passes: the pass's expressions in insertion order (SP_CAP rows) */
+  unsigned char* keep; /* sharded passes: done[i] takes part in the exchange */
   Row* ksend;          /* ... compacted rows / forms this rank sends */
   uint16_t* ksend_form;
   u64* keys[2];
   u32* idx[2];
-  u32* form_first;
-  u32* form_cnt;
-  u32* form_base;
-  u32* uniq_seq;
+  u32* uniq_seq;  /* new rows in value order: index of the row in done[] (tiny passes: insertion number) */
   u32* uniq_gap;
+  SeqKey* uniq_sk; /* ... and its insertion-order key (general passes) */
+  u64* hset[2];   /* per side (0 RHS, 1 LHS): hash set of the keys resident in the table, 4-slot buckets */
+  u32 hset_log2[2]; /* log2 of the number of buckets */
   Row* trow[2];
   double* tval[2];
   MatchEvent* events;
-  u64* tiles;     /* K1 look-back state, one word per tile */
-  Staged* staged; /* K1 scratch, 2 x EXP_MAX_ITEMS per block */
+  Staged* staged; /* K1 of the tiny passes: scratch, 2 x EXP_MAX_ITEMS */
   u64* rs_state;  /* radix look-back state, 256 words per chunk */
   u64* cc_state;  /* classify look-back state, one word per chunk */
   SortCtl* sortctl;

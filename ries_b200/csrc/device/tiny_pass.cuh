@@ -39,6 +39,7 @@ k_tiny_front(const DevPtrs* Dp, const PassArgs* Ap, PassCtl* ctl, TableState* T,
   }
   __threadfence();
   __syncthreads();
+  if (threadIdx.x == 0) ctl->gen = ctl->done_count; /* this K1 leaves no holes */
   stage_stamp(ctl, 1);
   if (ctl->overflow & OVF_SMALL) return; /* uniform */
   small_post_body(Dp, Ap, ctl, T);

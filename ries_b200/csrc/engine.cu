@@ -2,7 +2,8 @@
 //
 //   K1  k_expand            enumerate + evaluate one expression position of every live prefix
 //                           [ge_2 + exec, ries.c:8908-9475, 5308-5950]
-//   K2  k_reorder/k_rs_onesweep       stable LSD radix sort of the pass's survivors on the fp64 value
+//   K2  k_keys              sort keys; what the table already holds on this side is dropped by a hash probe
+//       k_rs_onesweep       LSD radix sort of the rest on the fp64 value
 //       k_classify_compact  duplicate pruning inside the pass and against the resident table
 //       k_match_merge_new, k_merge_old   merge into the resident sorted table   [bt_insert, ries.c:8622-8724]
 //   K3  k_match_merge_new   gap-local neighbour test with the derivative-scaled window
@@ -16,15 +17,17 @@
 // is captured once into a CUDA graph per expression length, and the host synchronises ONCE per pass
 // (to read counters and candidates for the sequential replay that decides the next pass).
 //
-// Files (one translation unit): device/state.cuh control blocks and pointer table; device/pass.cuh;
-// device/k1_expand.cuh; device/k2_sort.cuh (regroup + onesweep); device/k3_merge.cuh (classify, match +
-// merge-new); device/merge_old.cuh; device/small_pass.cuh (fused single-block path); device/shard.cuh (one
-// search over several GPUs); device/k4_refine.cuh; this file: buffers, graphs, the per-pass host loop.
+// Files (one translation unit): device/state.cuh control blocks, pointer table, insertion-order keys, hash set;
+// device/pass.cuh; device/k1_free.cuh (K1); device/k1_expand.cuh (K1 of the tiny passes); device/k2_sort.cuh (keys +
+// onesweep); device/k3_merge.cuh (classify, match + merge-new); device/merge_old.cuh; device/small_pass.cuh +
+// device/tiny_pass.cuh (single-block path); device/shard.cuh (one search over several GPUs); device/k4_refine.cuh;
+// this file: buffers, graphs, the per-pass host loop.
 //
 // Data layout in HBM (all device-resident for the whole search):
 //   nodes[]   48 B AoS, one per live prefix of the running pass (cactus stack, see params.h)
 //   table     rows 32 B AoS sorted by value + a dense 8 B key array for searches, ping-pong
-//   surv[]    32 B rows, the pass's complete expressions in insertion (DFS) order
+//   done[]    32 B rows + 2 B form index, the pass's complete expressions in NO particular order (state.cuh, SeqKey)
+//   hset[2]   per side, a hash set of the keys resident in the table (pre-dedupe before the sort)
 // No tensor cores: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -69,6 +72,7 @@ typedef unsigned int u32;
 #include "device/state.cuh"
 #include "device/pass.cuh"
 #include "device/k1_expand.cuh"
+#include "device/k1_free.cuh"
 #include "device/k2_sort.cuh"
 #include "device/k3_merge.cuh"
 #include "device/small_pass.cuh"
@@ -132,11 +136,10 @@ class DeviceEngine : public Engine {
     }
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     int occ = 1;
-    CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_DYN_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_DYN_SMEM));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, EXP_THREADS, EXP_DYN_SMEM));
-    if (occ < 1) occ = 1;
-    expand_grid_ = (u32)(num_sms_ * occ);
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xf_dyn_smem(XF_MAXQ)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    (void)occ;
     wide_grid_ = (u32)(num_sms_ * 8);
     use_graphs_ = getenv("RIES_NO_GRAPHS") == 0;
     use_small_post_ = getenv("RIES_NO_SMALL_POST") == 0; /* test hook: every pass through the general kernels */
@@ -150,7 +153,6 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaFuncSetAttribute(k_tiny_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TINY_DYN_SMEM));
     host_prof_ = getenv("RIES_HOST_PROF") != 0; /* host time per pass phase, printed at the next begin()/exit */
     pass_log_ = getenv("RIES_PASS_LOG") != 0; /* one line per pass on stderr: sizes and device time per stage */
-    CUDA_CHECK(cudaFuncSetAttribute(k_small_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_DYN_SMEM));
     CUDA_CHECK(cudaMalloc(&d_P_, sizeof(RiesParams)));
     CUDA_CHECK(cudaMalloc(&d_tt_, sizeof(TestTables)));
     CUDA_CHECK(cudaMalloc(&d_out_, sizeof(PassOut)));
@@ -182,9 +184,9 @@ class DeviceEngine : public Engine {
     const char* arena_env = getenv("RIES_ARENA_CAP"); /* test hook: start tiny to exercise overflow-and-rerun */
     const size_t arena0 = arena_env ? (size_t)atoi(arena_env) : (size_t)(1u << 20);
     const char* cap_env = getenv("RIES_EVENTS_CAP"); /* test hook: start tiny to exercise the regrow path */
-    staged_.ensure((size_t)expand_grid_ * 2 * EXP_MAX_ITEMS, st_);
+    staged_.ensure((size_t)2 * EXP_MAX_ITEMS, st_); /* K1 of the tiny passes: one block */
+    surv_.ensure(SP_CAP, st_);
     events_.ensure(std::max<size_t>(cap_env ? (size_t)atoi(cap_env) : (size_t)(1u << 14), 1), st_);
-    for (int i = 0; i < 3; i++) form_[i].ensure(4096, st_);
     grow_arena(arena0, arena0);
     ensure_table(1u << 16);
     ptrs_dirty_ = true;
@@ -192,12 +194,12 @@ class DeviceEngine : public Engine {
   ~DeviceEngine() override {
     cudaStreamSynchronize(st_);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
-    nodes_.release(st_); done_.release(st_); done_form_.release(st_); surv_.release(st_);
+    nodes_.release(st_); done_.release(st_); done_form_.release(st_); surv_.release(st_); uniq_sk_.release(st_);
+    hset_[0].release(st_); hset_[1].release(st_);
     for (int b = 0; b < 2; b++) { keys_[b].release(st_); idx_[b].release(st_); trow_[b].release(st_); tval_[b].release(st_); }
-    for (int i = 0; i < 3; i++) form_[i].release(st_);
-    uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); tiles_.release(st_); staged_.release(st_);
+    uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); staged_.release(st_);
     rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_); allctl_.release(st_);
-    surv_form_.release(st_); keep_.release(st_); ksend_.release(st_); ksend_form_.release(st_);
+    keep_.release(st_); ksend_.release(st_); ksend_form_.release(st_);
     cudaStreamSynchronize(st_);
     cudaFreeHost(h_allctl_);
     cudaFree(d_P_); cudaFree(d_tt_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
@@ -232,6 +234,21 @@ class DeviceEngine : public Engine {
     nt_ = 0;
     cur_ = 0;
     last_nu_ = 0;
+    reset_hash();
+    {
+      /* K1's operator queues: one per (complete?, enabled symbol); their number sets the kernel's shared memory
+         and with it the grid (blocks per SM) and the captured launch sequences */
+      const int nq = 2 * (P.cls_n[0] + P.cls_n[1] + P.cls_n[2]);
+      if (nq != k1_nq_) {
+        for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+        graphs_.clear();
+        k1_nq_ = nq;
+        int occ = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, XF_THREADS, xf_dyn_smem(nq)));
+        if (occ < 1) occ = 1;
+        expand_grid_ = (u32)(num_sms_ * occ);
+      }
+    }
     prev_nodes_[0] = prev_nodes_[1] = prev_done_[0] = prev_done_[1] = 0;
     kernel_launches = 0;
     h2d_bytes = sizeof(P);
@@ -246,13 +263,38 @@ class DeviceEngine : public Engine {
     stage_events_ = getenv("RIES_STAGE_EVENTS") != 0;
   }
 
-  long inserted_before(uint32_t seq, bool inclusive) override {
+  /* host-side twin of seq_before (state.cuh): a was inserted before b */
+  static bool sym_before_host(const Sym128& a, const Sym128& b) {
+    for (int i = 0; i < RIES_MAX_ELEN + 1; i++) {
+      const unsigned ca = sym_get(a, i), cb = sym_get(b, i);
+      if (ca != cb) return ca < cb;
+    }
+    return false;
+  }
+  static bool seq_before_host(u32 fa, const Sym128& a, u32 fb, const Sym128& b) {
+    return fa != fb ? fa < fb : sym_before_host(a, b);
+  }
+
+  long inserted_before(const MatchEvent& ev, bool inclusive) override {
     if (!last_nu_) return 0;
-    std::vector<u32> h(last_nu_);
-    CUDA_CHECK(cudaMemcpyAsync(h.data(), uniq_seq_.p, last_nu_ * sizeof(u32), cudaMemcpyDeviceToHost, st_));
-    CUDA_CHECK(cudaStreamSynchronize(st_));
     long c = 0;
-    for (u32 s : h) c += inclusive ? (s <= seq) : (s < seq);
+    if (last_tiny_) { /* tiny passes number their expressions in insertion order */
+      std::vector<u32> h(last_nu_);
+      CUDA_CHECK(cudaMemcpyAsync(h.data(), uniq_seq_.p, last_nu_ * sizeof(u32), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      for (u32 s : h) c += inclusive ? (s <= ev.seq) : (s < ev.seq);
+      return c;
+    }
+    std::vector<SeqKey> h(last_nu_);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), uniq_sk_.p, last_nu_ * sizeof(SeqKey), cudaMemcpyDeviceToHost, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    const Sym128& me = last_using_x_ ? ev.lhs.sym : ev.rhs.sym; /* the NEW expression of the event */
+    for (const SeqKey& k : h) {
+      Sym128 ks; ks.lo = k.lo; ks.hi = k.hi;
+      const bool before = seq_before_host(k.form, ks, ev.seq, me);
+      const bool same = k.form == ev.seq && ks.lo == me.lo && ks.hi == me.hi;
+      c += (before || (inclusive && same)) ? 1 : 0;
+    }
     return c;
   }
 
@@ -268,19 +310,17 @@ class DeviceEngine : public Engine {
     }
     int max_len = 0;
     for (const FormDesc& f : forms) max_len = std::max(max_len, (int)f.flen);
-    for (int i = 0; i < 3; i++)
-      if (form_[i].ensure(nforms, st_)) ptrs_dirty_ = true;
     if (nodes_.cap < (size_t)nforms + 16) grow_arena(nforms + 16, done_.cap);
     memcpy(h_forms_, forms.data(), nforms * sizeof(FormDesc)); /* pinned; the last pass's copy has completed */
     h2d_bytes += nforms * sizeof(FormDesc) + sizeof(PassArgs);
 
-    bool no_small_post = !use_small_post_;
+    const int side = using_x ? 1 : 0;
+    bool no_tiny = !use_small_post_;
     unsigned long long gen_k1 = 0; /* sharded passes: complete expressions of all ranks' K1, before the pre-dedupe */
     bool was_sharded = false, was_tiny = false;
     {
       /* sizes grow ~1.3-1.6x per complexity step: keep twice the previous same-side pass in hand, so that
          the overflow-and-rerun path stays the exception (it costs a whole pass) */
-      const int side = using_x ? 1 : 0;
       const size_t want_nodes = (size_t)prev_nodes_[side] * 2, want_done = (size_t)prev_done_[side] * 2;
       if (!getenv("RIES_ARENA_CAP") && (want_nodes > nodes_.cap || want_done > done_.cap))
         grow_arena(std::max(want_nodes, nodes_.cap), std::max(want_done, done_.cap));
@@ -288,6 +328,7 @@ class DeviceEngine : public Engine {
     while (true) {
       /* the merged table needs room for every survivor the arena can hold */
       ensure_table((size_t)nt_ + done_.cap);
+      ensure_hash(side);
       if (ptrs_dirty_) upload_ptrs();
       h_args_->using_x = using_x; h_args_->cplx = cplx; h_args_->skip_exact = skip_exact ? 1 : 0;
       h_args_->nforms = (int)nforms; h_args_->best_match0 = best_match0;
@@ -295,21 +336,20 @@ class DeviceEngine : public Engine {
       h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
       h_args_->cap_events = (u32)events_.cap; h_args_->seq = ++pass_seq_;
       /* size class from the previous pass of the same side (sizes grow ~1.3-1.6x per complexity step) */
-      int small = (prev_nodes_[using_x ? 1 : 0] <= 12000 && prev_done_[using_x ? 1 : 0] <= 3000) ? 1 : 0;
-      if (small && !no_small_post && prev_done_[using_x ? 1 : 0] <= SP_CAP / 3 && nt_ <= 200000u) small = 2;
-      if (force_small_post_ && !no_small_post) small = 2; /* test hook: mispredict, to exercise the rerun */
+      const int small = (prev_nodes_[side] <= 12000 && prev_done_[side] <= 3000) ? 1 : 0;
       /* one search over several GPUs: only passes big enough to pay for the exchange are sharded */
       const DistState& ds = dist_state();
       const int shard_world = ds.fake_world > 1 ? ds.fake_world : ds.world;
-      const bool shard = shard_world > 1 && prev_done_[using_x ? 1 : 0] >= shard_min_;
+      const bool shard = shard_world > 1 && prev_done_[side] >= shard_min_;
       h_args_->shard_rank = (shard && ds.fake_world <= 1) ? ds.rank : 0;
       h_args_->shard_world = shard ? shard_world : 1;
       h_args_->gathered = 0; /* a sharded pass switches to the gathered arrays after the exchange */
       h_args_->pad2 = 0;
-      if (shard && small == 2) small = 1; /* the single-block kernel has no local/global split */
-      /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh) */
-      const bool tiny = use_tiny_ && !stage_events_ && small == 2 && !force_small_post_ && !shard &&
-                        prev_nodes_[using_x ? 1 : 0] <= tiny_nodes_;
+      /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh); force_small_post_ is the
+         test hook that mispredicts, to exercise the rerun through the general kernels */
+      const bool tiny = !shard && !no_tiny && !stage_events_ &&
+                        (force_small_post_ || (use_tiny_ && small && prev_done_[side] <= SP_CAP / 3 && nt_ <= 200000u &&
+                                               prev_nodes_[side] <= tiny_nodes_));
       CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                  cudaMemcpyHostToDevice, st_));
       was_tiny = tiny;
@@ -360,25 +400,34 @@ class DeviceEngine : public Engine {
       if (ovf & (OVF_NODES | OVF_DONE)) grow_arena(want_nodes, want_done);
       if (ovf & OVF_EVENTS) {
         if (events_.ensure((size_t)h_ctl_->n_events + 1024, st_)) ptrs_dirty_ = true;
+        /* the merge kernels had already entered this pass's new keys into the hash set, but the table was not
+           flipped: forget them, or the rerun's pre-dedupe would drop the very rows it has to insert */
+        rebuild_hash(0);
+        rebuild_hash(1);
       }
-      if (ovf & OVF_SMALL) no_small_post = true;
+      if (ovf & OVF_SMALL) no_tiny = true;
     }
-    const u32 n = h_ctl_->done_count, nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
+    const u32 nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
     const double hp_t4 = host_prof_ ? now_us() : 0;
+    const unsigned long long gen = was_sharded ? gen_k1 : h_ctl_->gen;
     if (pass_log_) {
       const float* ms = last_ms_;
-      fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
-              using_x ? (was_tiny ? "lhs" : "LHS") : (was_tiny ? "rhs" : "RHS"), cplx, nforms, max_len, h_ctl_->node_count, n, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
+      fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9llu keys %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
+              using_x ? (was_tiny ? "lhs" : "LHS") : (was_tiny ? "rhs" : "RHS"), cplx, nforms, max_len, h_ctl_->node_count, gen,
+              was_tiny ? h_ctl_->done_count : h_ctl_->n_keys, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
     }
-    const unsigned long long gen = was_sharded ? gen_k1 : (unsigned long long)n;
-    prev_nodes_[using_x ? 1 : 0] = h_ctl_->node_count;
-    prev_done_[using_x ? 1 : 0] = (u32)std::min<unsigned long long>(gen, 0xffffffffull);
+    prev_nodes_[side] = h_ctl_->node_count;
+    prev_done_[side] = (u32)std::min<unsigned long long>(std::max<unsigned long long>(gen, was_sharded ? 0 : h_ctl_->done_count), 0xffffffffull);
+    prev_new_[side] = nu;
+    side_rows_[side] += nu;
     expand_nodes += h_ctl_->node_count;
-    sort_keys += n;
+    sort_keys += was_tiny ? h_ctl_->done_count : h_ctl_->n_keys;
     out.generated = (double)gen;
     out.dead_ends = (double)h_ctl_->dead;
     out.inserted = (long)nu;
     last_nu_ = nu;
+    last_tiny_ = was_tiny;
+    last_using_x_ = using_x != 0;
     if (nu) {
       merge_rows += (unsigned long long)nt_ + nu;
       cur_ ^= 1;
@@ -398,9 +447,20 @@ class DeviceEngine : public Engine {
         d2h_bytes += (unsigned long long)ne * sizeof(MatchEvent);
         out.events.assign(h_events_, h_events_ + ne);
       }
-      std::sort(out.events.begin(), out.events.end(), [](const MatchEvent& a, const MatchEvent& b) {
-        return a.seq != b.seq ? a.seq < b.seq : a.kind < b.kind;
-      });
+      /* replay order = insertion order of the NEW expression, then exact < previous < next (check_sides) */
+      if (was_tiny) {
+        std::sort(out.events.begin(), out.events.end(), [](const MatchEvent& a, const MatchEvent& b) {
+          return a.seq != b.seq ? a.seq < b.seq : a.kind < b.kind;
+        });
+      } else {
+        const bool ux = using_x != 0;
+        std::sort(out.events.begin(), out.events.end(), [ux](const MatchEvent& a, const MatchEvent& b) {
+          const Sym128& sa = ux ? a.lhs.sym : a.rhs.sym;
+          const Sym128& sb = ux ? b.lhs.sym : b.rhs.sym;
+          if (a.seq != b.seq || sa.lo != sb.lo || sa.hi != sb.hi) return seq_before_host(a.seq, sa, b.seq, sb);
+          return a.kind < b.kind;
+        });
+      }
     }
     if (host_prof_ && hp_t1 > 0) {
       hp_[0] += hp_t1 - hp_t0; hp_[1] += hp_t2 - hp_t1; hp_[2] += hp_t3 - hp_t2; hp_[3] += hp_t4 - hp_t3;
@@ -458,6 +518,7 @@ class DeviceEngine : public Engine {
        exit at once costs more than the work itself.  A wrong prediction is slow, never wrong. */
     const u32 g_exp = small ? 24u : expand_grid_;
     const u32 g_wide = small ? 12u : wide_grid_;
+    const u32 g_keys = small ? 12u : (u32)num_sms_ * 4;
     const u32 g_sort = small ? 12u : (u32)num_sms_ * RS_MIN_BLOCKS;
     switch (stage) {
       case 0:
@@ -466,7 +527,7 @@ class DeviceEngine : public Engine {
           /* positions after the first may overlap their prologue with the previous position's tail
              (programmatic dependent launch; the kernel waits on the dependency itself) */
           cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3(g_exp); cfg.blockDim = dim3(EXP_THREADS); cfg.dynamicSmemBytes = EXP_DYN_SMEM; cfg.stream = st_;
+          cfg.gridDim = dim3(g_exp); cfg.blockDim = dim3(XF_THREADS); cfg.dynamicSmemBytes = xf_dyn_smem(k1_nq_); cfg.stream = st_;
           cudaLaunchAttribute at[1];
           at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
           at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -476,21 +537,11 @@ class DeviceEngine : public Engine {
         }
         break;
       case 1:
-        if (small == 2) {
-          k_small_post<<<1, SP_THREADS, SP_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-          break;
-        }
-        k_form_bounds<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
-        k_form_scan<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
-        k_reorder<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
+        k_keys<<<g_keys, KK_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         for (int pass = 0; pass < 8; pass++)
           k_rs_onesweep<<<g_sort, RS_THREADS, RS_DYN_SMEM, st_>>>(d_ptrs_, d_ctl_, d_tab_, pass);
         break;
       case 2:
-        if (small == 2) {
-          k_merge_old<<<48u, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
-          break;
-        }
         k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_merge_old<<<small ? 48u : wide_grid_, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
@@ -523,7 +574,7 @@ class DeviceEngine : public Engine {
       if (!use_graphs_) {
         enqueue_stage(stage, max_len, small);
       } else {
-        const int key = ((stage == 0) ? max_len : -stage) * 4 + ((stage == 0 && small == 2) ? 1 : small) + 1000;
+        const int key = ((stage == 0) ? max_len : -stage) * 4 + small + 1000;
         auto it = graphs_.find(key);
         if (it == graphs_.end()) {
           cudaGraph_t g;
@@ -538,9 +589,7 @@ class DeviceEngine : public Engine {
         CUDA_CHECK(cudaGraphLaunch(it->second, st_));
       }
       if (events) CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
-      const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1
-                                 : (stage == 1) ? ((small == 2) ? 1 : 11)
-                                 : (stage == 2) ? ((small == 2) ? 1 : 3) : 2;
+      const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1 : (stage == 1) ? 9 : (stage == 2) ? 3 : 2;
       kernel_launches += k;
       stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
     }
@@ -628,9 +677,11 @@ class DeviceEngine : public Engine {
     ch |= keep_.ensure(done_.cap, st_);
     ch |= ksend_.ensure(done_.cap, st_);
     ch |= ksend_form_.ensure(done_.cap, st_);
+    ch |= gdone_.ensure(1, st_);
+    ch |= gdone_form_.ensure(1, st_);
     if (ch) { ptrs_dirty_ = true; upload_ptrs(); }
     const u32 g_wide = small ? 12u : wide_grid_;
-    /* K1 -> regroup + sort of this rank's own expressions -> drop what cannot matter -> compact */
+    /* K1 -> keys (hash pre-dedupe) + sort of this rank's own expressions -> drop what cannot matter -> compact */
     auto local_front = [&]() {
       launch_stages(0, 1, max_len, small, true);
       k_local_filter<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
@@ -708,10 +759,12 @@ class DeviceEngine : public Engine {
        here on the regroup kernels read the gathered arrays */
     PassCtl t = all[0];
     unsigned long long nodes = 0, done = 0, kept = 0, dead = 0;
-    for (int r = 0; r < world; r++) { nodes += all[r].node_count; done += all[r].done_count; kept += all[r].n_kept; dead += all[r].dead; }
+    for (int r = 0; r < world; r++) { nodes += all[r].node_count; done += all[r].gen; kept += all[r].n_kept; dead += all[r].dead; }
     t.node_count = (u32)std::min<unsigned long long>(nodes, 0xffffffffull);
-    t.done_count = (u32)kept;
+    t.done_count = (u32)kept; /* the gathered rows have no holes */
+    t.gen = done;
     t.dead = dead;
+    t.n_keys = 0;
     t.lvl_begin = t.lvl_end = 0; t.tile_ticket = 0; t.blocks_done = 0; t.chunk_ticket = 0; t.aux_ticket = 0;
     *gen_k1 = done;
     *h_ctl_ = t;
@@ -722,19 +775,47 @@ class DeviceEngine : public Engine {
     return 0;
   }
 
+  /* The hash sets restart small with every search and grow with the side's row count: at most half full after
+     the coming pass (estimated from the side's last pass; an underestimate only costs filtering), a quarter
+     full right after growing.  Growing means: clear, then re-enter the side's keys from the table. */
+  void reset_hash() {
+    for (int sd = 0; sd < 2; sd++) {
+      hset_log2_[sd] = 12;
+      if (hset_[sd].ensure((size_t)4 << hset_log2_[sd], st_)) ptrs_dirty_ = true;
+      CUDA_CHECK(cudaMemsetAsync(hset_[sd].p, 0, ((size_t)4 << hset_log2_[sd]) * sizeof(u64), st_));
+      side_rows_[sd] = 0;
+      prev_new_[sd] = 0;
+    }
+    ptrs_dirty_ = true;
+  }
+  void rebuild_hash(int sd) {
+    if (ptrs_dirty_) upload_ptrs();
+    CUDA_CHECK(cudaMemsetAsync(hset_[sd].p, 0, ((size_t)4 << hset_log2_[sd]) * sizeof(u64), st_));
+    if (nt_) k_hset_rebuild<<<(u32)num_sms_ * 8, 256, 0, st_>>>(d_ptrs_, d_tab_, sd);
+    kernel_launches += nt_ ? 1 : 0;
+  }
+  void ensure_hash(int sd) {
+    const size_t expect = side_rows_[sd] + 3 * (size_t)prev_new_[sd] + 4096;
+    if (expect * 2 <= ((size_t)4 << hset_log2_[sd])) return;
+    u32 lg = hset_log2_[sd];
+    while (expect * 4 > ((size_t)4 << lg) && lg < 30) lg++;
+    hset_log2_[sd] = lg;
+    hset_[sd].ensure((size_t)4 << lg, st_);
+    ptrs_dirty_ = true;
+    rebuild_hash(sd);
+  }
+
   /* nodes / done arenas and everything sized by them */
   void grow_arena(size_t want_nodes, size_t want_done) {
     bool ch = false;
     ch |= nodes_.ensure(want_nodes, st_);
     ch |= done_.ensure(want_done, st_);
     ch |= done_form_.ensure(done_.cap, st_);
-    ch |= surv_.ensure(done_.cap, st_);
-    ch |= surv_form_.ensure(done_.cap, st_);
     for (int b = 0; b < 2; b++) { ch |= keys_[b].ensure(done_.cap, st_); ch |= idx_[b].ensure(done_.cap, st_); }
     ch |= uniq_seq_.ensure(done_.cap, st_);
     ch |= uniq_gap_.ensure(done_.cap, st_);
+    ch |= uniq_sk_.ensure(done_.cap, st_);
     /* look-back state must start as zeros (stale bits must not look like a live epoch / status) */
-    ch |= tiles_.ensure(nodes_.cap / EXP_PARENTS + 2, st_, false, true);
     ch |= rs_state_.ensure((done_.cap / RS_CHUNK + 2) * 256, st_, false, true);
     ch |= cc_state_.ensure(done_.cap / 256 + 2, st_, false, true); /* one word per chunk; the smallest chunk is 256 (k_compact_kept) */
     if (ch) ptrs_dirty_ = true;
@@ -750,10 +831,10 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
     DevPtrs& h = *h_ptrs_;
     h.P = d_P_; h.tt = d_tt_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
-    h.surv_form = surv_form_.p; h.keep = keep_.p; h.ksend = ksend_.p; h.ksend_form = ksend_form_.p;
+    h.keep = keep_.p; h.ksend = ksend_.p; h.ksend_form = ksend_form_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
-    h.form_first = form_[0].p; h.form_cnt = form_[1].p; h.form_base = form_[2].p;
-    h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.events = events_.p; h.tiles = tiles_.p; h.staged = staged_.p;
+    h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.uniq_sk = uniq_sk_.p; h.events = events_.p; h.staged = staged_.p;
+    for (int sd = 0; sd < 2; sd++) { h.hset[sd] = hset_[sd].p; h.hset_log2[sd] = hset_log2_[sd]; }
     h.rs_state = rs_state_.p; h.cc_state = cc_state_.p; h.sortctl = d_sortctl_; h.opcnt = d_opcnt_;
     h.host_out = d_host_out_;
     CUDA_CHECK(cudaMemcpyAsync(d_ptrs_, h_ptrs_, sizeof(DevPtrs), cudaMemcpyHostToDevice, st_));
@@ -763,6 +844,7 @@ class DeviceEngine : public Engine {
   cudaStream_t st_;
   int num_sms_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
+  int k1_nq_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
   bool use_tiny_ = true, host_prof_ = false, use_pdl_ = true, stage_events_ = false;
   double hp_[6] = {0, 0, 0, 0, 0, 0}; /* prepare, enqueue, wait, collect, events, passes */
@@ -801,14 +883,20 @@ class DeviceEngine : public Engine {
   FormDesc* h_forms_ = 0;
   DevBuf<Node> nodes_;
   DevBuf<Row> done_, surv_, gdone_, ksend_;
-  DevBuf<uint16_t> done_form_, gdone_form_, surv_form_, ksend_form_;
+  DevBuf<uint16_t> done_form_, gdone_form_, ksend_form_;
+  DevBuf<SeqKey> uniq_sk_;
+  /* per side: hash set of the table's keys (state.cuh); rows that side holds, new rows of its last pass */
+  DevBuf<u64> hset_[2];
+  u32 hset_log2_[2] = {0, 0};
+  size_t side_rows_[2] = {0, 0};
+  u32 prev_new_[2] = {0, 0};
+  bool last_tiny_ = false, last_using_x_ = false;
   DevBuf<unsigned char> keep_;
   DevBuf<PassCtl> allctl_;
   PassCtl* h_allctl_ = 0; /* pinned, MAX_RANKS entries */
   u32 shard_min_ = 100000; /* complete expressions in the previous same-side pass from which a pass is sharded */
-  DevBuf<u64> tiles_, rs_state_, cc_state_;
+  DevBuf<u64> rs_state_, cc_state_;
   DevBuf<Staged> staged_;
-  DevBuf<u32> form_[3];
   DevBuf<u64> keys_[2];
   DevBuf<u32> idx_[2];
   DevBuf<u32> uniq_seq_, uniq_gap_;

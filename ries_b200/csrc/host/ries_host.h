@@ -133,8 +133,9 @@ class Engine {
   virtual void begin(const RiesParams& P) = 0;
   virtual void run_pass(int using_x, int cplx, const std::vector<FormDesc>& forms,
                         double best_match0, bool skip_exact, PassOutput& out) = 0;
-  /* rows of the last pass inserted with seq < `seq` (or <= when inclusive): early-exit accounting */
-  virtual long inserted_before(uint32_t seq, bool inclusive) = 0;
+  /* rows of the last pass inserted before the new expression of candidate `ev` (or up to and including it):
+     early-exit accounting */
+  virtual long inserted_before(const MatchEvent& ev, bool inclusive) = 0;
   virtual const char* name() const = 0;
 };
 

@@ -464,7 +464,7 @@ struct Search {
     if (!cur_ev) return resident_rows;
     /* An EXACT event's expression is never inserted; a neighbour event fires right after its
        expression was inserted (bt_insert 8686-8721). */
-    return resident_rows + eng.inserted_before(cur_ev->seq, cur_ev->kind != EV_EXACT);
+    return resident_rows + eng.inserted_before(*cur_ev, cur_ev->kind != EV_EXACT);
   }
 
   void print_end(int exit_code) { /* ries.c:7574 */

@@ -82,7 +82,8 @@ def test_gpu_stats_are_consistent(product_lib):
     st = ries_b200.last_stats()
     assert st["kernel_launches"] > 0
     assert st["lhs_distinct"] <= st["lhs_expressions"] and st["rhs_distinct"] <= st["rhs_expressions"]
-    assert st["sort_keys"] == st["lhs_expressions"] + st["rhs_expressions"]
+    # what the table already holds on the same side is dropped before the sort (hash pre-dedupe)
+    assert st["lhs_distinct"] + st["rhs_distinct"] <= st["sort_keys"] <= st["lhs_expressions"] + st["rhs_expressions"]
 
 
 def test_gpu_candidate_buffer_regrow(product_lib):
