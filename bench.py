@@ -301,7 +301,8 @@ def batch_object(args, ries_b200, rank, world, dist, torch):
                         "%d GPU(s)" % (args.batch_size, BATCH_SEED, level, args.workers, world),
             "targets": int(nt), "seconds": wall, "targets_per_sec": nt / wall, "targets_per_sec_per_gpu": nt / wall / world,
             "expr_per_sec": exprs / wall, "reports_checked_against_reference": int(checked),
-            "reports_identical": int(same), "api": "ries_batch(targets, flags, workers, done_cb) via ctypes"}
+            "reports_identical": int(same), "shared_rhs": ries_b200.batch_shared_stats(),
+            "api": "ries_batch(targets, flags, workers, done_cb) via ctypes"}
 
 
 def main():

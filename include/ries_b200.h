@@ -68,6 +68,14 @@ typedef void (*ries_batch_done_fn)(void *ctx, int index, int exit_code, const ch
 int ries_batch(int n_targets, const char *const *targets, int n_flags, const char *const *flags,
                int n_workers, ries_batch_done_fn done, void *ctx);
 
+/* The targets of a batch whose search parameters differ in the target alone share ONE enumeration of every
+ * right-hand-side pass (BASELINE config 5: "sharing one RHS database"): the pass is run once, by the first worker
+ * that needs it, and every target filters it by its own overflow bound (public/ries.c:12250, 9020); everything
+ * after enumeration stays per target, so each report is still byte-identical to `ries <flags> t`.  Counters of the
+ * most recent ries_batch() call: RHS passes enumerated for the batch, RHS passes of targets served from them.
+ * (RIES_BATCH_NO_SHARE=1 in the environment switches the sharing off.) */
+void ries_batch_shared_stats(unsigned long long *passes_built, unsigned long long *passes_taken);
+
 /* ONE search sharded over the GPUs of one box (north_star row (e); the reference is single-threaded, there is
  * nothing to cite): one process per GPU, each calls ries_main() with the same argv after joining an NCCL
  * communicator.  The forms of every large pass are dealt round-robin to the ranks for enumerate+evaluate,

@@ -126,6 +126,16 @@ def batch(targets, flags=("-F3",), workers=8):
     return out
 
 
+def batch_shared_stats():
+    """RHS passes enumerated once for the last batch, and RHS passes of its targets served from them."""
+    lib = _load()
+    a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib.ries_batch_shared_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.ries_batch_shared_stats.restype = None
+    lib.ries_batch_shared_stats(ctypes.byref(a), ctypes.byref(b))
+    return {"rhs_passes_enumerated_once": a.value, "rhs_passes_served": b.value}
+
+
 def fp64_peak_tflops():
     return _load().ries_fp64_peak_tflops()
 

@@ -130,6 +130,11 @@ void append_sink(void* ctx, const char* buf, size_t n) { static_cast<std::string
 
 /* Engines of the batch workers, kept across calls (device buffers, pinned memory, CUDA graphs: building one costs
    more than a -l2 search).  A worker takes one for the whole call and hands it back at the end. */
+static unsigned long long g_batch_shared_built = 0, g_batch_shared_used = 0;
+extern "C" void ries_batch_shared_stats(unsigned long long* passes_built, unsigned long long* passes_taken) {
+  if (passes_built) *passes_built = g_batch_shared_built;
+  if (passes_taken) *passes_taken = g_batch_shared_used;
+}
 static std::mutex g_pool_mu;
 static std::vector<ries::Engine*> g_pool;
 
@@ -164,8 +169,45 @@ extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags
   if (n_workers > n_targets) n_workers = n_targets;
   std::atomic<int> next(0), failures(0);
   std::mutex mu;
+  /* One RHS database for the batch (BASELINE config 5): the targets whose search parameters differ in the target
+     alone share one enumeration of every right-hand-side pass (engine.cu, SharedRhs).  Planned here from the
+     command lines: the common parameters, and the range of overflow bounds p_ovr = |T| / k_prune_deriv the shared
+     passes must serve.  Targets more than four decades below the largest one (one in ten thousand of a uniform
+     batch) would make every pass keep records for that much of its tail, so they search on their own. */
+  void* shared = 0;
+  if (n_targets >= 2 && !getenv("RIES_BATCH_NO_SHARE")) {
+    std::vector<::RiesParams> ps((size_t)n_targets);
+    std::vector<char> ok((size_t)n_targets, 0);
+    for (int i = 0; i < n_targets; i++) {
+      std::vector<std::string> args;
+      args.push_back("ries");
+      for (int k = 0; k < n_flags; k++) args.push_back(flags[k]);
+      args.push_back(targets[i]);
+      std::vector<char*> argv;
+      for (auto& a : args) argv.push_back(&a[0]);
+      ok[i] = ries::search_params((int)argv.size(), argv.data(), &ps[i]) ? 1 : 0;
+    }
+    int first = -1;
+    for (int i = 0; i < n_targets && first < 0; i++) if (ok[i]) first = i;
+    if (first >= 0) {
+      const ::RiesParams sig = ries::shared_rhs_signature(ps[first]);
+      double p_max = 0;
+      for (int i = 0; i < n_targets; i++) {
+        if (!ok[i]) continue;
+        const ::RiesParams si = ries::shared_rhs_signature(ps[i]);
+        ok[i] = memcmp(&si, &sig, sizeof(sig)) == 0 && ps[i].p_ovr > 0 && ps[i].p_ovr < 1e300;
+        if (ok[i] && ps[i].p_ovr > p_max) p_max = ps[i].p_ovr;
+      }
+      double p_min = p_max;
+      int sharing = 0;
+      for (int i = 0; i < n_targets; i++)
+        if (ok[i] && ps[i].p_ovr >= p_max * 1e-4) { sharing++; if (ps[i].p_ovr < p_min) p_min = ps[i].p_ovr; }
+      if (sharing >= 2) shared = ries::shared_rhs_create(sig, p_max, p_min);
+    }
+  }
   auto worker = [&]() {
     ries::Engine* eng = pool_take();
+    if (eng) eng->set_shared(shared);
     while (true) {
       int i = next.fetch_add(1);
       if (i >= n_targets) break;
@@ -188,21 +230,28 @@ extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags
           if (code == 1 && opt.got_target) { /* out of device memory: do not reuse half-grown buffers */
             delete eng;
             eng = pool_take();
+            if (eng) eng->set_shared(shared);
           }
         } catch (...) {
           code = 3;
           delete eng;
           eng = pool_take();
+          if (eng) eng->set_shared(shared);
         }
       }
       if (code != 0 && code != RIES_EXIT_NO_ERROR) failures++;
       std::lock_guard<std::mutex> lock(mu);
       if (done) done(ctx, i, code, text.data(), text.size());
     }
+    if (eng) eng->set_shared(0);
     pool_give(eng);
   };
   std::vector<std::thread> pool;
   for (int w = 0; w < n_workers; w++) pool.emplace_back(worker);
   for (auto& t : pool) t.join();
+  if (shared) {
+    ries::shared_rhs_stats(shared, &g_batch_shared_built, &g_batch_shared_used);
+    ries::shared_rhs_destroy(shared);
+  }
   return failures.load();
 }

@@ -199,8 +199,12 @@ RIES_HD int canon_apply(const RiesParams& P, bool do_dx, const Sym128& sym, int 
    (8962-9076) and the complete-expression tests (9085-9139).  `nodes` is the pass's node arena
    (parents of every level stay resident for `below` links); `par_idx` is the parent's own index.
    Fills only the evaluation part of `child` (val, der, tag, below, sp). */
+/* `track_m` (RHS passes of a batch that shares its right-hand sides, engine.cu SharedRhs): an RHS prefix has no
+   derivative, and its `der` field carries instead M = the largest |value| any exec() along the prefix has
+   produced -- what decides, target by target, whether the prefix survives that target's overflow bound
+   (|v| >= p_ovr, ries.c:9020).  The operands then enter exec() with derivative 0, as they would have. */
 RIES_HD int expand_exec(const RiesParams& P, int cls, int g, bool complete, const Node* nodes,
-                        const Node& par, uint32_t par_idx, int using_x, Node& child) {
+                        const Node& par, uint32_t par_idx, int using_x, Node& child, bool track_m = false) {
   unsigned char sym = P.sym_char[g];
   Val r;
   int err;
@@ -211,14 +215,14 @@ RIES_HD int expand_exec(const RiesParams& P, int cls, int g, bool complete, cons
     below = par_idx;
     sp = par.sp + 1;
   } else if (cls == 1) {
-    Val a = {par.val, par.der, par.tag};
+    Val a = {par.val, track_m ? 0.0 : par.der, par.tag};
     err = exec_unary(P, sym, using_x != 0, a, r);
     below = par.below;
     sp = par.sp;
   } else {
     const Node& lo = nodes[par.below];
-    Val a = {lo.val, lo.der, lo.tag};
-    Val b = {par.val, par.der, par.tag};
+    Val a = {lo.val, track_m ? 0.0 : lo.der, lo.tag};
+    Val b = {par.val, track_m ? 0.0 : par.der, par.tag};
     err = exec_binary(P, sym, using_x != 0, a, b, r);
     below = lo.below;
     sp = par.sp - 1;
@@ -237,6 +241,7 @@ RIES_HD int expand_exec(const RiesParams& P, int cls, int g, bool complete, cons
     if ((sp == 1) && (fabs(r.d) / (1.0 + fabs(r.v)) < P.k_vanished_dx)) return OUT_DEAD;
   }
   child.pad0 = 0;
+  const double m_here = track_m ? fmax(par.der, fabs(r.v)) : 0.0; /* canonval's results are not overflow-tested */
   if (complete) {
     /* complete expression (9085-9139) */
     if (using_x && (fabs(r.d) < P.k_vanished_dx)) return OUT_DEAD;
@@ -252,7 +257,7 @@ RIES_HD int expand_exec(const RiesParams& P, int cls, int g, bool complete, cons
     }
   }
   child.val = r.v;
-  child.der = r.d;
+  child.der = track_m ? m_here : r.d;
   child.tag = (uint8_t)r.tag;
   child.below = below;
   child.sp = (uint8_t)sp;

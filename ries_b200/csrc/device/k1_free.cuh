@@ -35,6 +35,12 @@
 #define XF_CAP (XF_TILE + 32) /* a queue holds at most 31 left-overs + one tile's pairs of that symbol */
 #define XF_MAXQ (2 * RIES_MAX_SYMS)
 
+__device__ __forceinline__ void push_tail(TailRec* tail, u32 cap, PassCtl* ctl, double lo, double hi, int val) {
+  const u32 e = atomicAdd(&ctl->n_tail, 1u);
+  if (e < cap) { TailRec r; r.lo = lo; r.hi = hi; r.val = val; r.pad = 0; tail[e] = r; }
+  else atomicOr(&ctl->overflow, OVF_TAIL);
+}
+
 /* dynamic shared memory: nq queues of XF_CAP entries (u32: index of the prefix in the node arena) */
 __host__ __device__ inline size_t xf_dyn_smem(int nq) { return (size_t)nq * XF_CAP * sizeof(u32); }
 
@@ -77,6 +83,10 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
   const u32 ntiles = (n + XF_TILE - 1) / XF_TILE;
   const int using_x = Ap->using_x, cplx = Ap->cplx;
   const u32 cap_nodes = Ap->cap_nodes, cap_done = Ap->cap_done;
+  /* shared RHS pass (SharedRhs, engine.cu): M rides in `der`; records for what depends on a target's bound */
+  const bool track_m = Ap->track_m != 0;
+  const double p_min = Ap->p_min;
+  const u32 cap_tail = Ap->cap_tail;
   /* queue of (complete, class, slot) = complete * nsq + qoff[class] + slot; symbol of queue q = sym_of_q */
   const u32 qoff1 = (u32)P.cls_n[0], qoff2 = qoff1 + (u32)P.cls_n[1], nsq = qoff2 + (u32)P.cls_n[2];
   const u32 nq = 2 * nsq;
@@ -105,6 +115,8 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
             const int atts = prefix_attrs(P, F, par, using_x);
             u32 mask = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
             my_dead += (u32)ns - (u32)__popc(mask);
+            if (track_m && par.der >= p_min && (u32)ns != (u32)__popc(mask)) /* gone with the prefix, for a smaller bound */
+              push_tail(D.tail, cap_tail, ctl, -1.0 / 0.0, par.der, -(int)((u32)ns - (u32)__popc(mask)));
             const u32 q0 = ((par.len + 1 >= F.flen) ? nsq : 0u) + (cls == 0 ? 0u : cls == 1 ? qoff1 : qoff2);
             while (mask) {
               const u32 k = (u32)__ffs((int)mask) - 1;
@@ -206,8 +218,13 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
         if (act) {
           const u32 p = s_ent[q * XF_CAP + (head[q] + j0) % XF_CAP];
           par = nodes[p];
-          oc = expand_exec(P, cls, g, complete, nodes, par, p, using_x, child);
+          oc = expand_exec(P, cls, g, complete, nodes, par, p, using_x, child, track_m);
           if (oc == OUT_DEAD) my_dead++;
+          if (track_m) {
+            if (oc == OUT_DEAD) { if (par.der >= p_min) push_tail(D.tail, cap_tail, ctl, -1.0 / 0.0, par.der, -1); }
+            else if ((oc == OUT_LIVE || oc == OUT_DONE) && child.der >= p_min) /* one dead-end where the bound cuts in */
+              push_tail(D.tail, cap_tail, ctl, par.der, child.der, 1);
+          }
         }
         while (s_alloc_tag != (par2 << 30) + tile + 1) {} /* set long ago, as a rule */
         if (!complete) {

@@ -3,7 +3,7 @@
 #pragma once
 
 /* ------------------------------------------------ sort keys + pre-dedupe ------------------- */
-__device__ __forceinline__ bool pass_ok(const PassCtl* C) { return (C->overflow & (OVF_NODES | OVF_DONE)) == 0; }
+__device__ __forceinline__ bool pass_ok(const PassCtl* C) { return (C->overflow & (OVF_NODES | OVF_DONE | OVF_KEPT)) == 0; }
 
 __device__ __forceinline__ u64 key_of(double v) { /* order-preserving map double -> u64 */
   u64 b = (u64)__double_as_longlong(v);
@@ -16,8 +16,7 @@ __device__ __forceinline__ u64 key_of(double v) { /* order-preserving map double
    counted.  At -l6 that is 70-84 % of what the big passes generate, found here with ONE 32-byte probe of the
    side's hash set instead of eight digit passes and a table search.  The survivors are compacted (block
    aggregate, one atomic per 1024 slots; their order is free: insertion order is recovered from (form, symbols)
-   wherever it matters) together with the histograms of all eight key digits for the radix sort below.
-   Sharded passes: keep[] is cleared for every slot (k_local_filter sets the winners). */
+   wherever it matters) together with the histograms of all eight key digits for the radix sort below. */
 #define KK_THREADS 256
 #define KK_ITEMS 4
 #define KK_CHUNK (KK_THREADS * KK_ITEMS)
@@ -26,7 +25,7 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
   __shared__ u32 s_h[8][256];
   __shared__ u32 s_cnt[KK_ITEMS * (KK_THREADS / 32)];
   __shared__ u32 s_base;
-  stage_stamp(C, 1);
+  if (!A->gathered) stage_stamp(C, 1); /* a sharded pass: k_keys_send has stamped the end of K1 */
   if (!pass_ok(C)) return;
   const u32 n = C->done_count;
   if ((u64)blockIdx.x * KK_CHUNK >= n) return;
@@ -37,7 +36,10 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
   const int side = A->using_x ? 1 : 0;
   const u64* __restrict__ hs = Dp->hset[side];
   const u32 hlog = Dp->hset_log2[side];
-  const bool clear_keep = A->shard_world > 1 && !A->gathered;
+  /* gathered rows of a sharded pass: slot j of rank r is filled iff j < that rank's count */
+  const bool gathered = A->gathered != 0;
+  const u32 bound = gathered ? (u32)A->shard_bound : 1u;
+  const SlotHdr* __restrict__ ghdr = D.ghdr;
   u64* keys = D.keys[0];
   u32* idx = D.idx[0];
   for (int d = 0; d < 8; d++) s_h[d][tid] = 0;
@@ -51,8 +53,8 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
       bool keep = false;
       k[r] = 0;
       if (i < n) {
-        if (clear_keep) D.keep[i] = 0;
-        if (done_form[i] != FORM_HOLE) {
+        const bool filled = gathered ? (i % bound) < ghdr[i / bound].n_kept : done_form[i] != FORM_HOLE;
+        if (filled) {
           k[r] = key_of(done[i].val);
           keep = !hset_contains(hs, hlog, k[r]);
         }
@@ -87,6 +89,97 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
     }
     __syncthreads();
   }
+  SortCtl* ctl = D.sortctl;
+  for (int d = 0; d < 8; d++) {
+    u32 c = s_h[d][tid];
+    if (c) atomicAdd(&ctl->ghist[d][tid], c);
+  }
+}
+
+/* k_keys for the consumer of a shared RHS pass: the rows come from the batch's enumeration; a row exists for this
+   target iff M < its overflow bound (that many are "generated"); what the hash probe lets through is copied into
+   this engine's done[] with `der` back to 0 (der == 0 <=> RHS everywhere downstream). */
+__global__ void __launch_bounds__(KK_THREADS)
+k_keys_shared(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const SharedView* Vp) {
+  const SharedView V = *Vp;
+  __shared__ u32 s_h[8][256];
+  __shared__ u32 s_cnt[KK_ITEMS * (KK_THREADS / 32)];
+  __shared__ u32 s_base, s_gen;
+  stage_stamp(C, 1);
+  const u32 n = V.n_slots;
+  if ((u64)blockIdx.x * KK_CHUNK >= n) return;
+  const DevPtrs& D = *Dp;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64* __restrict__ hs = Dp->hset[0];
+  const u32 hlog = Dp->hset_log2[0];
+  const u32 cap_done = A->cap_done;
+  u64* keys = D.keys[0];
+  u32* idx = D.idx[0];
+  for (int d = 0; d < 8; d++) s_h[d][tid] = 0;
+  if (tid == 0) s_gen = 0;
+  __syncthreads();
+  u32 my_gen = 0;
+  for (u32 base = blockIdx.x * KK_CHUNK; base < n; base += gridDim.x * KK_CHUNK) {
+    u64 k[KK_ITEMS];
+    u32 flags = 0;
+#pragma unroll
+    for (int r = 0; r < KK_ITEMS; r++) {
+      const u32 i = base + r * KK_THREADS + tid;
+      bool keep = false;
+      k[r] = 0;
+      if (i < n && V.forms[i] != FORM_HOLE) {
+        const Row row = V.rows[i];
+        if (row.der < V.p_t) {
+          my_gen++;
+          k[r] = key_of(row.val);
+          keep = !hset_contains(hs, hlog, k[r]);
+        }
+      }
+      const u32 b = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_cnt[r * (KK_THREADS / 32) + warp] = __popc(b);
+      if (keep) flags |= (1u << r) | (__popc(b & ((1u << lane) - 1)) << (8 + 6 * r));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const u32 c = s_cnt[lane];
+      u32 inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += v;
+      }
+      s_cnt[lane] = inc - c;
+      if (lane == 31) {
+        const u32 b0 = inc ? atomicAdd(&C->n_keys, inc) : 0;
+        if (inc && (u64)b0 + inc > cap_done) { atomicOr(&C->overflow, OVF_DONE); atomicMax(&C->done_count, b0 + inc); }
+        s_base = b0;
+      }
+    }
+    __syncthreads();
+    const u32 cbase = s_base;
+#pragma unroll
+    for (int r = 0; r < KK_ITEMS; r++) {
+      if ((flags >> r) & 1u) {
+        const u32 pos = cbase + s_cnt[r * (KK_THREADS / 32) + warp] + ((flags >> (8 + 6 * r)) & 63u);
+        if (pos < cap_done) {
+          const u32 i = base + r * KK_THREADS + tid;
+          Row row = V.rows[i];
+          row.der = 0.0;
+          D.done[pos] = row;
+          D.done_form[pos] = V.forms[i];
+          keys[pos] = k[r];
+          idx[pos] = pos;
+#pragma unroll
+          for (int d = 0; d < 8; d++) atomicAdd(&s_h[d][(u32)(k[r] >> (8 * d)) & 255u], 1u);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) my_gen += __shfl_xor_sync(0xffffffffu, my_gen, o);
+  if (lane == 0 && my_gen) atomicAdd(&s_gen, my_gen);
+  __syncthreads();
+  if (tid == 0 && s_gen) atomicAdd((unsigned long long*)&C->gen, (unsigned long long)s_gen);
   SortCtl* ctl = D.sortctl;
   for (int d = 0; d < 8; d++) {
     u32 c = s_h[d][tid];

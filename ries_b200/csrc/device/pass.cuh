@@ -20,7 +20,7 @@ __device__ __forceinline__ void pass_begin_body(const DevPtrs* D, const PassArgs
   if (threadIdx.x == 0) {
     C->lvl_begin = 0; C->lvl_end = nroots; C->node_count = nroots; C->done_count = 0;
     C->tile_ticket = 0; C->blocks_done = 0; C->n_events = 0; C->n_uniq = 0; C->overflow = 0;
-    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0; C->n_keys = 0; C->gen = 0;
+    C->chunk_ticket = 0; C->nt_before = T->nt; C->dead = 0; C->aux_ticket = 0; C->n_kept = 0; C->n_keys = 0; C->gen = 0; C->n_tail = 0; C->max_nodes = 0; C->max_done = 0;
     C->stamp[1] = C->stamp[2] = C->stamp[3] = C->stamp[4] = 0;
     u32 e = (T->epoch + 16) & 0x3ffffff0u; /* 16 tags per pass: 8 radix digits + classify */
     if (e == 0) e = 16;
@@ -73,4 +73,29 @@ __global__ void k_pass_end(const DevPtrs* D, const PassArgs* A, PassCtl* C, Tabl
   __syncthreads();
   stage_stamp(C, 4);
   post_to_host(D, A, C);
+}
+
+/* Consumer side of a shared RHS pass (engine.cu SharedRhs): instead of K1, the pass starts from the batch's
+   enumeration.  Control block reset as in k_pass_begin; the dead-end count is the shared pass's, corrected for this
+   target's overflow bound by the records that apply to it. */
+__global__ void k_shared_front(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T, const SharedView* Vp) {
+  const SharedView V = *Vp;
+  __shared__ long long s_sum[32];
+  stage_stamp(C, 0);
+  pass_begin_body(D, A, C, T);
+  long long acc = 0;
+  for (u32 i = threadIdx.x; i < V.n_tail; i += blockDim.x) {
+    const TailRec r = V.tail[i];
+    if (r.lo < V.p_t && V.p_t <= r.hi) acc += r.val;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (u32 w = 0; w < (blockDim.x + 31) / 32; w++) tot += s_sum[w];
+    C->dead = (u64)((long long)V.dead_base + tot);
+    C->node_count = V.node_count;
+    C->lvl_begin = C->lvl_end = 0;
+  }
 }

@@ -8,6 +8,32 @@
 #define OVF_DONE 2u
 #define OVF_EVENTS 4u
 #define OVF_SMALL 8u /* a pass predicted small was not: rerun it through the general kernels */
+#define OVF_KEPT 16u /* sharded passes: a rank's send slot was too small */
+#define OVF_TAIL 32u /* shared RHS pass: the list of bound-dependent records was too small */
+
+/* One bound-dependent correction of a shared RHS pass's dead-end count: it applies to a target whose overflow
+   bound P satisfies lo < P <= hi (see k1_free.cuh and DESIGN.md section 7). */
+struct TailRec {
+  double lo, hi;
+  int val, pad;
+};
+
+/* A shared RHS pass as its consumers see it (engine.cu SharedRhs; passed to the kernels by value). */
+struct SharedView {
+  const Row* rows;         /* val, M (in `der`), symbols; slots may be holes */
+  const uint16_t* forms;
+  const TailRec* tail;
+  u32 n_slots, n_tail, node_count, pad;
+  u64 dead_base;           /* dead-ends under the largest bound of the batch */
+  double p_t;              /* this target's bound */
+};
+
+/* Header of a rank's send slot in the exchange of a sharded pass (shard.cuh). */
+struct __attribute__((aligned(16))) SlotHdr {
+  u32 n_kept, overflow, node_count, done_slots;
+  u64 dead, gen;
+  u32 pad[8];
+};
 
 struct SortCtl {
   u32 ghist[8][256];
@@ -28,7 +54,14 @@ struct PassArgs {
   u32 seq; /* number of this pass launch: the last kernel posts it to the host together with the results */
   /* one search over several GPUs: this rank enumerates the forms f with f % shard_world == shard_rank, and
      the regroup kernels read the all-gathered complete expressions instead of this rank's own */
-  int shard_rank, shard_world, gathered, pad2;
+  int shard_rank, shard_world, gathered;
+  int shard_bound; /* rows per rank in the exchange of a sharded pass (send slot, stride of the gathered array) */
+  /* RHS pass enumerated once for a whole batch of targets (engine.cu, SharedRhs): `der` of an RHS prefix carries
+     M = max |value| along the prefix, and what depends on a target's overflow bound is recorded (TailRec) for
+     every prefix / child with M >= p_min, the smallest bound in the batch */
+  int track_m;
+  u32 cap_tail;
+  double p_min;
 };
 
 /* Written by the kernels of a pass; copied back to pinned host memory at its end. */
@@ -46,6 +79,8 @@ struct PassCtl {
   u32 aux_ticket;         /* k_local_filter / k_compact_kept (sharded passes) */
   u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
   u64 gen;                /* complete expressions generated (g_ne, ries.c:9190): done_count counts SLOTS, holes included */
+  u32 max_nodes, max_done; /* sharded passes: the largest rank's node and expression slots (arena sizing) */
+  u32 n_tail, pad_tail;    /* TailRec records written (may exceed the capacity: then OVF_TAIL is set) */
   /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] regroup +
      sort, [2] classify/match/merge, [3] refine, [4] end.  Written by thread 0 of block 0 of the stage's first
      kernel (the kernels of a pass run back to back on one stream), read by the host from the copied-back
@@ -70,9 +105,12 @@ struct PassOut {
   u32 pad[3];
 };
 
-/* What the host sends per pass, in one copy: the scalars, then the forms. */
+/* What the host sends per pass, in one copy: the scalars, (the view of a shared RHS pass,) then the forms. */
+#define PASSIN_VIEW_OFFSET 128
 #define PASSIN_FORMS_OFFSET 256
 #define PASSIN_MAX_FORMS 65536
+static_assert(sizeof(PassArgs) <= PASSIN_VIEW_OFFSET, "PassArgs outgrew its slot in the pass block");
+static_assert(sizeof(SharedView) <= PASSIN_FORMS_OFFSET - PASSIN_VIEW_OFFSET, "SharedView outgrew its slot in the pass block");
 
 /* Survives passes. */
 struct TableState {
@@ -155,12 +193,14 @@ struct DevPtrs {
   Node* nodes;
   Row* done;
   uint16_t* done_form;
-  Row* gdone;           /* all ranks' complete expressions, rank-major (sharded passes only) */
+  Row* gdone;           /* all ranks' send slots, rank r at [r * shard_bound ...) (sharded passes only) */
   uint16_t* gdone_form;
   Row* surv;           /* tiny passes: the pass's expressions in insertion order (SP_CAP rows) */
-  unsigned char* keep; /* sharded passes: done[i] takes part in the exchange */
-  Row* ksend;          /* ... compacted rows / forms this rank sends */
+  Row* ksend;          /* sharded passes: this rank's send slot (rows, form indices, header) */
   uint16_t* ksend_form;
+  SlotHdr* shdr;
+  SlotHdr* ghdr;
+  TailRec* tail;  /* shared RHS passes being built: bound-dependent records */ /* ... and the gathered headers, one per rank */
   u64* keys[2];
   u32* idx[2];
   u32* uniq_seq;  /* new rows in value order: index of the row in done[] (tiny passes: insertion number) */

@@ -37,7 +37,9 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "core/expand.h"
@@ -110,6 +112,58 @@ struct DevBuf {
 };
 
 
+/* ---------------------------------------------------------------- one RHS database per batch ---- */
+/* BASELINE config 5: "a batch of targets sharing one RHS database".  Right-hand sides contain no x, and what the
+   reference does with them depends on the target in exactly three ways: (1) the overflow bound
+   p_ovr = |T| / k_prune_deriv cuts every prefix whose value reaches it (ries.c:12250, test at 9020) -- so the set
+   of generated expressions and the dead-end counters shrink with |T|; (2) an RHS value equal to an LHS value
+   already in the tree is reported, not inserted (8648-8661); (3) the scheduler interleaves the sides by their
+   insert counts (12424-12460).  (2) and (3) happen AFTER enumeration, so what is shared here is the enumeration:
+   the RHS pass of a complexity is run ONCE per batch, by whichever engine needs it first, under the batch's
+   largest bound, with every prefix carrying M = the largest |value| along it.  A target with bound P then takes the
+   rows with M < P (exactly the expressions its own run would have generated; their number is its "expressions"
+   count), and its dead-end count is the shared one corrected by the recorded cases where P cuts in (TailRec).
+   Everything after that -- pre-dedupe against ITS table, sort, cross-side exact matches, neighbour tests, merge --
+   is the target's own pipeline, unchanged.  Reports stay byte-identical (tests: 64 targets against the reference). */
+struct SharedPass {
+  Row* rows = 0;
+  uint16_t* forms = 0;
+  TailRec* tail = 0;
+  u32 n_slots = 0, n_tail = 0, node_count = 0;
+  u64 dead_base = 0, gen = 0;
+};
+struct SharedRhs {
+  std::mutex mu;
+  std::map<int, SharedPass> passes;
+  RiesParams sig;
+  double p_max = 0, p_min = 0;
+  int c_share = -1; /* RHS passes from this complexity on are shared (set by the first engine that gets there) */
+  int dev = 0;
+  std::atomic<unsigned long long> built{0}, consumed{0};
+  ~SharedRhs() {
+    cudaSetDevice(dev);
+    for (auto& kv : passes) { cudaFree(kv.second.rows); cudaFree(kv.second.forms); cudaFree(kv.second.tail); }
+  }
+};
+
+RiesParams shared_rhs_signature(const RiesParams& P) {
+  RiesParams s = P;
+  s.target = 0; s.p_ovr = 0; s.n_ovr = 0; s.targ_tags = 0;
+  return s;
+}
+void* shared_rhs_create(const RiesParams& sig, double p_max, double p_min) {
+  SharedRhs* r = new SharedRhs();
+  r->sig = sig; r->p_max = p_max; r->p_min = p_min;
+  const char* dev_env = getenv("RIES_DEVICE");
+  r->dev = dev_env ? atoi(dev_env) : 0;
+  return r;
+}
+void shared_rhs_destroy(void* ctx) { delete static_cast<SharedRhs*>(ctx); }
+void shared_rhs_stats(void* ctx, unsigned long long* b, unsigned long long* c) {
+  SharedRhs* r = static_cast<SharedRhs*>(ctx);
+  *b = r->built.load(); *c = r->consumed.load();
+}
+
 class DeviceEngine : public Engine {
  public:
   DeviceEngine() {
@@ -123,6 +177,7 @@ class DeviceEngine : public Engine {
     const char* dev_env = getenv("RIES_DEVICE");
     int dev = dev_env ? atoi(dev_env) : 0;
     CUDA_CHECK(cudaSetDevice(dev));
+    dev_ = dev;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     num_sms_ = prop.multiProcessorCount;
@@ -176,7 +231,10 @@ class DeviceEngine : public Engine {
     h_args_ = (PassArgs*)h_passin_;
     h_forms_ = (FormDesc*)(h_passin_ + PASSIN_FORMS_OFFSET);
     CUDA_CHECK(cudaMallocHost(&h_ptrs_, sizeof(DevPtrs)));
-    CUDA_CHECK(cudaMallocHost(&h_allctl_, RIES_MAX_RANKS * sizeof(PassCtl)));
+    CUDA_CHECK(cudaMallocHost(&h_args2_, sizeof(PassArgs)));
+    CUDA_CHECK(cudaMalloc(&d_shdr_, sizeof(SlotHdr)));
+    CUDA_CHECK(cudaMalloc(&d_ghdr_, RIES_MAX_RANKS * sizeof(SlotHdr)));
+    CUDA_CHECK(cudaMemset(d_ghdr_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
     if (const char* e = getenv("RIES_SHARD_MIN")) shard_min_ = (u32)atol(e);
     memset(h_ptrs_, 0, sizeof(DevPtrs));
     for (int i = 0; i < 5; i++) CUDA_CHECK(cudaEventCreate(&ev_[i]));
@@ -192,16 +250,17 @@ class DeviceEngine : public Engine {
     ptrs_dirty_ = true;
   }
   ~DeviceEngine() override {
+    cudaSetDevice(dev_);
     cudaStreamSynchronize(st_);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
     nodes_.release(st_); done_.release(st_); done_form_.release(st_); surv_.release(st_); uniq_sk_.release(st_);
-    hset_[0].release(st_); hset_[1].release(st_);
+    hset_[0].release(st_); hset_[1].release(st_); tail_.release(st_);
     for (int b = 0; b < 2; b++) { keys_[b].release(st_); idx_[b].release(st_); trow_[b].release(st_); tval_[b].release(st_); }
     uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); staged_.release(st_);
-    rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_); allctl_.release(st_);
-    keep_.release(st_); ksend_.release(st_); ksend_form_.release(st_);
+    rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_);
+    ksend_.release(st_); ksend_form_.release(st_);
     cudaStreamSynchronize(st_);
-    cudaFreeHost(h_allctl_);
+    cudaFreeHost(h_args2_); cudaFree(d_shdr_); cudaFree(d_ghdr_);
     cudaFree(d_P_); cudaFree(d_tt_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
     cudaFree(d_opcnt_);
     cudaFreeHost(h_out_); cudaFreeHost(h_passin_); cudaFreeHost(h_ptrs_);
@@ -211,8 +270,11 @@ class DeviceEngine : public Engine {
     cudaStreamDestroy(st_);
   }
   const char* name() const override { return "sm_100a"; }
+  void set_shared(void* ctx) override { shared_ = static_cast<SharedRhs*>(ctx); }
 
   void begin(const RiesParams& P) override {
+    /* the calling thread may be a new one (batch workers take pooled engines): its current device is 0 */
+    CUDA_CHECK(cudaSetDevice(dev_));
     if (host_prof_ && hp_[5] > 0) {
       fprintf(stderr, "host per pass (us): prepare %.1f enqueue %.1f wait %.1f collect %.1f events %.1f over %.0f passes\n",
               hp_[0] / hp_[5], hp_[1] / hp_[5], hp_[2] / hp_[5], hp_[3] / hp_[5], hp_[4] / hp_[5], hp_[5]);
@@ -235,6 +297,14 @@ class DeviceEngine : public Engine {
     cur_ = 0;
     last_nu_ = 0;
     reset_hash();
+    cur_P_ = P;
+    /* this search may use the batch's RHS enumeration iff it differs from the batch's common parameters in the
+       target alone and its overflow bound lies in the range the shared passes keep records for */
+    shared_ok_ = false;
+    if (shared_ && !P.canon_ops && dist_state().world <= 1 && dist_state().fake_world <= 1) {
+      const RiesParams sg = shared_rhs_signature(P);
+      shared_ok_ = memcmp(&sg, &shared_->sig, sizeof(RiesParams)) == 0 && P.p_ovr <= shared_->p_max && P.p_ovr >= shared_->p_min;
+    }
     {
       /* K1's operator queues: one per (complete?, enabled symbol); their number sets the kernel's shared memory
          and with it the grid (blocks per SM) and the captured launch sequences */
@@ -250,6 +320,7 @@ class DeviceEngine : public Engine {
       }
     }
     prev_nodes_[0] = prev_nodes_[1] = prev_done_[0] = prev_done_[1] = 0;
+    prev_gen_[0] = prev_gen_[1] = prev_keys_[0] = prev_keys_[1] = shard_kept_[0] = shard_kept_[1] = 0;
     kernel_launches = 0;
     h2d_bytes = sizeof(P);
     d2h_bytes = 0;
@@ -317,7 +388,7 @@ class DeviceEngine : public Engine {
     const int side = using_x ? 1 : 0;
     bool no_tiny = !use_small_post_;
     unsigned long long gen_k1 = 0; /* sharded passes: complete expressions of all ranks' K1, before the pre-dedupe */
-    bool was_sharded = false, was_tiny = false;
+    bool was_sharded = false, was_tiny = false, was_shared = false;
     {
       /* sizes grow ~1.3-1.6x per complexity step: keep twice the previous same-side pass in hand, so that
          the overflow-and-rerun path stays the exception (it costs a whole pass) */
@@ -340,11 +411,13 @@ class DeviceEngine : public Engine {
       /* one search over several GPUs: only passes big enough to pay for the exchange are sharded */
       const DistState& ds = dist_state();
       const int shard_world = ds.fake_world > 1 ? ds.fake_world : ds.world;
-      const bool shard = shard_world > 1 && prev_done_[side] >= shard_min_;
+      const bool shard = shard_world > 1 && prev_gen_[side] >= shard_min_;
       h_args_->shard_rank = (shard && ds.fake_world <= 1) ? ds.rank : 0;
       h_args_->shard_world = shard ? shard_world : 1;
       h_args_->gathered = 0; /* a sharded pass switches to the gathered arrays after the exchange */
-      h_args_->pad2 = 0;
+      const u32 bound = shard ? shard_bound(side, shard_world) : 0;
+      h_args_->shard_bound = (int)bound;
+      h_args_->track_m = 0; h_args_->cap_tail = 0; h_args_->p_min = 0;
       /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh); force_small_post_ is the
          test hook that mispredicts, to exercise the rerun through the general kernels */
       const bool tiny = !shard && !no_tiny && !stage_events_ &&
@@ -353,7 +426,33 @@ class DeviceEngine : public Engine {
       CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                  cudaMemcpyHostToDevice, st_));
       was_tiny = tiny;
-      if (tiny) {
+      const bool use_shared = !tiny && !shard && shared_wanted(using_x, cplx, side);
+      was_shared = use_shared;
+      if (use_shared) {
+        const SharedPass sp = shared_get(cplx, forms, max_len);
+        /* the build above may have used the pass's argument block: (re)send it */
+        h_args_->using_x = 0; h_args_->cplx = cplx; h_args_->skip_exact = skip_exact ? 1 : 0;
+        h_args_->nforms = (int)nforms; h_args_->best_match0 = best_match0;
+        h_args_->cap_nodes = (u32)std::min<size_t>(nodes_.cap, 0xffffffffu);
+        h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
+        h_args_->cap_events = (u32)events_.cap; h_args_->seq = ++pass_seq_;
+        h_args_->shard_rank = 0; h_args_->shard_world = 1; h_args_->gathered = 0; h_args_->shard_bound = 0;
+        h_args_->track_m = 0; h_args_->cap_tail = 0; h_args_->p_min = 0;
+        if (ptrs_dirty_) upload_ptrs();
+        SharedView& V = *(SharedView*)(h_passin_ + PASSIN_VIEW_OFFSET);
+        V.rows = sp.rows; V.forms = sp.forms; V.tail = sp.tail; V.n_slots = sp.n_slots; V.n_tail = sp.n_tail;
+        V.node_count = sp.node_count; V.pad = 0; V.dead_base = sp.dead_base; V.p_t = cur_P_.p_ovr;
+        CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
+                                   cudaMemcpyHostToDevice, st_));
+        if (host_prof_) hp_t1 = now_us();
+        launch_stages(4, 4, max_len, small, false); /* the shared front: control block, keys, sort */
+        launch_stages(2, 3, max_len, small, false);
+        if (host_prof_) hp_t2 = now_us();
+        wait_pass();
+        if (host_prof_) hp_t3 = now_us();
+        collect_stamp_times();
+        shared_->consumed++;
+      } else if (tiny) {
         if (host_prof_) hp_t1 = now_us();
         launch_tiny();
         if (host_prof_) hp_t2 = now_us();
@@ -369,35 +468,37 @@ class DeviceEngine : public Engine {
         if (host_prof_) hp_t3 = now_us();
         if (stage_events_) collect_stage_times(0, 3); else collect_stamp_times();
       } else {
-        size_t want_nodes = nodes_.cap, want_done = done_.cap;
-        const u32 fovf = sharded_front(max_len, small, &want_nodes, &want_done, &gen_k1);
-        if (fovf) {
-          grow_arena(std::max(want_nodes, nodes_.cap * ((fovf & OVF_NODES) ? 2 : 1)),
-                     std::max(want_done, done_.cap * ((fovf & OVF_DONE) ? 2 : 1)));
-          continue;
-        }
-        sharded_passes++;
-        was_sharded = true;
-        launch_stages(1, 3, max_len, small, true);
-        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, offsetof(PassOut, seq), cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        CUDA_CHECK(cudaGetLastError());
-        d2h_bytes += offsetof(PassOut, seq);
-        collect_stage_times(1, 3);
+        /* one search over several GPUs: the front on this rank's forms, the fixed-size exchange, the replicated
+           back half -- all enqueued at once, no host round trip in between (shard.cuh) */
+        if (host_prof_) hp_t1 = now_us();
+        sharded_front(max_len, small, bound, shard_world);
+        launch_stages(1, 3, max_len, small, false);
+        if (host_prof_) hp_t2 = now_us();
+        wait_pass();
+        if (host_prof_) hp_t3 = now_us();
+        collect_stamp_times();
         if (gather_pending_) {
+          CUDA_CHECK(cudaEventSynchronize(ev_g_[1]));
           float ms = 0;
           if (cudaEventElapsedTime(&ms, ev_g_[0], ev_g_[1]) == cudaSuccess) gather_ms += ms;
           (void)cudaGetLastError();
           gather_pending_ = false;
+        }
+        was_sharded = true;
+        if (!h_ctl_->overflow) {
+          sharded_passes++;
+          gather_bytes += (unsigned long long)shard_world * bound * (sizeof(Row) + sizeof(uint16_t));
         }
       }
       const u32 ovf = h_ctl_->overflow;
       if (!ovf) break;
       /* grow what overflowed and rerun the pass; the live table buffer has not been touched */
       size_t want_nodes = nodes_.cap, want_done = done_.cap;
-      if (ovf & OVF_NODES) want_nodes = std::max<size_t>(nodes_.cap * 2, (size_t)h_ctl_->node_count * 2);
-      if (ovf & OVF_DONE) want_done = std::max<size_t>(done_.cap * 2, (size_t)h_ctl_->done_count * 2);
+      /* a sharded pass reports the largest rank's sizes (every rank sees the same gathered headers) */
+      if (ovf & OVF_NODES) want_nodes = std::max<size_t>(nodes_.cap * 2, (size_t)(was_sharded ? h_ctl_->max_nodes : h_ctl_->node_count) * 2);
+      if (ovf & OVF_DONE) want_done = std::max<size_t>(done_.cap * 2, (size_t)(was_sharded ? h_ctl_->max_done : h_ctl_->done_count) * 2);
       if (ovf & (OVF_NODES | OVF_DONE)) grow_arena(want_nodes, want_done);
+      if (ovf & OVF_KEPT) shard_kept_[side] = std::max<u32>(h_ctl_->n_kept, shard_kept_[side] * 2);
       if (ovf & OVF_EVENTS) {
         if (events_.ensure((size_t)h_ctl_->n_events + 1024, st_)) ptrs_dirty_ = true;
         /* the merge kernels had already entered this pass's new keys into the hash set, but the table was not
@@ -409,15 +510,23 @@ class DeviceEngine : public Engine {
     }
     const u32 nu = h_ctl_->n_uniq, ne = h_ctl_->n_events;
     const double hp_t4 = host_prof_ ? now_us() : 0;
-    const unsigned long long gen = was_sharded ? gen_k1 : h_ctl_->gen;
+    const unsigned long long gen = h_ctl_->gen;
+    (void)gen_k1;
     if (pass_log_) {
       const float* ms = last_ms_;
       fprintf(stderr, "pass %s cplx %3d forms %5u len %2d nodes %9u done %9llu keys %9u new %8u table %9u events %5u | K1 %7.3f sort %7.3f merge %7.3f refine %6.3f ms\n",
               using_x ? (was_tiny ? "lhs" : "LHS") : (was_tiny ? "rhs" : "RHS"), cplx, nforms, max_len, h_ctl_->node_count, gen,
               was_tiny ? h_ctl_->done_count : h_ctl_->n_keys, nu, nt_, ne, ms[0], ms[1], ms[2], ms[3]);
     }
-    prev_nodes_[side] = h_ctl_->node_count;
-    prev_done_[side] = (u32)std::min<unsigned long long>(std::max<unsigned long long>(gen, was_sharded ? 0 : h_ctl_->done_count), 0xffffffffull);
+    /* sizes for the next pass of this side; a sharded pass sizes the arenas by its largest rank */
+    if (was_shared) { /* the consumer of a shared pass only holds what survived its pre-dedupe */
+      h_ctl_->done_count = std::max(h_ctl_->done_count, h_ctl_->n_keys);
+    }
+    prev_nodes_[side] = was_sharded ? h_ctl_->max_nodes : h_ctl_->node_count;
+    prev_done_[side] = was_sharded ? h_ctl_->max_done : (u32)std::min<unsigned long long>(std::max<unsigned long long>(gen, h_ctl_->done_count), 0xffffffffull);
+    prev_gen_[side] = (u32)std::min<unsigned long long>(gen, 0xffffffffull);
+    prev_keys_[side] = h_ctl_->n_keys;
+    shard_kept_[side] = was_sharded ? h_ctl_->n_kept : 0;
     prev_new_[side] = nu;
     side_rows_[side] += nu;
     expand_nodes += h_ctl_->node_count;
@@ -546,10 +655,18 @@ class DeviceEngine : public Engine {
         k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_merge_old<<<small ? 48u : wide_grid_, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
         break;
-      default:
+      case 3:
         k_refine<<<small ? 8 : 64, 64, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
         k_pass_end<<<1, 128, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         break;
+      default: { /* 4: a shared RHS pass's front (instead of stages 0 and 1): the view rides in the pass's argument block */
+        const SharedView* vp = (const SharedView*)(d_passin_ + PASSIN_VIEW_OFFSET);
+        k_shared_front<<<1, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, vp);
+        k_keys_shared<<<g_keys, KK_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, vp);
+        for (int pass = 0; pass < 8; pass++)
+          k_rs_onesweep<<<g_sort, RS_THREADS, RS_DYN_SMEM, st_>>>(d_ptrs_, d_ctl_, d_tab_, pass);
+        break;
+      }
     }
   }
 
@@ -568,7 +685,7 @@ class DeviceEngine : public Engine {
      the kernels leave in the control block (collect_stamp_times); only sharded passes, whose stages are
      interleaved with the exchange, bracket them with CUDA events (ev_[k] before stage k and after the last). */
   void launch_stages(int first, int last, int max_len, int small, bool events = false) {
-    if (first == 0) bump_epoch();
+    if (first == 0 || first == 4) bump_epoch();
     if (events) CUDA_CHECK(cudaEventRecord(ev_[first], st_));
     for (int stage = first; stage <= last; stage++) {
       if (!use_graphs_) {
@@ -589,9 +706,10 @@ class DeviceEngine : public Engine {
         CUDA_CHECK(cudaGraphLaunch(it->second, st_));
       }
       if (events) CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
-      const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1 : (stage == 1) ? 9 : (stage == 2) ? 3 : 2;
+      const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1 : (stage == 1) ? 9 : (stage == 2) ? 3 : (stage == 3) ? 2 : 10;
       kernel_launches += k;
-      stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
+      if (stage == 4) { stage_launches[0] += 1; stage_launches[1] += 9; }
+      else stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
     }
   }
 
@@ -663,116 +781,136 @@ class DeviceEngine : public Engine {
     (void)cudaGetLastError();
   }
 
-  /* Front half of a pass sharded over `world` ranks (or virtual ranks): K1 on this rank's forms, the local
-     regroup + sort + pre-dedupe (k_local_filter), then the all-gather of what is left into
-     gdone/gdone_form in rank-major order and the totals into the device control block.  Returns the
-     overflow flags (any rank's); on overflow nothing was gathered and *want_* hold the sizes to grow to.
-     Every rank computes the same totals, so every rank takes the same decisions afterwards. */
-  u32 sharded_front(int max_len, int small, size_t* want_nodes, size_t* want_done, unsigned long long* gen_k1) {
+  /* Is the coming RHS pass taken from the batch's shared enumeration?  Shared from the first complexity at which
+     some engine of the batch finds a pass worth it (a tiny pass costs less than the bookkeeping). */
+  bool shared_wanted(int using_x, int cplx, int side) {
+    if (!shared_ok_ || using_x) return false;
+    std::lock_guard<std::mutex> lock(shared_->mu);
+    if (shared_->c_share < 0 && prev_gen_[side] >= 2048) shared_->c_share = cplx;
+    return shared_->c_share >= 0 && cplx >= shared_->c_share;
+  }
+
+  /* The shared RHS pass of complexity `cplx`; the first engine to ask enumerates it (K1 with the batch's largest
+     overflow bound, M carried in `der`, bound-dependent records) and keeps a copy for the whole batch. */
+  SharedPass shared_get(int cplx, const std::vector<FormDesc>& forms, int max_len) {
+    std::lock_guard<std::mutex> lock(shared_->mu);
+    auto it = shared_->passes.find(cplx);
+    if (it != shared_->passes.end()) return it->second;
+    const u32 nforms = (u32)forms.size();
+    /* sizes from the previous shared pass (RHS passes grow ~1.3x per complexity step) */
+    size_t want_nodes = nodes_.cap, want_done = done_.cap, want_tail = std::max<size_t>(tail_.cap, 1u << 16);
+    auto pv = shared_->passes.find(cplx - 1);
+    if (pv != shared_->passes.end()) {
+      want_nodes = std::max<size_t>(want_nodes, (size_t)pv->second.node_count * 2);
+      want_done = std::max<size_t>(want_done, (size_t)pv->second.n_slots * 2);
+      want_tail = std::max<size_t>(want_tail, (size_t)pv->second.n_tail * 2 + 4096);
+    }
+    RiesParams P2 = cur_P_;
+    P2.p_ovr = shared_->p_max; P2.n_ovr = -shared_->p_max;
+    CUDA_CHECK(cudaMemcpyAsync(d_P_, &P2, sizeof(P2), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    PassCtl c;
+    while (true) {
+      if (want_nodes > nodes_.cap || want_done > done_.cap) grow_arena(std::max(want_nodes, nodes_.cap), std::max(want_done, done_.cap));
+      if (tail_.ensure(want_tail, st_)) ptrs_dirty_ = true;
+      if (ptrs_dirty_) upload_ptrs();
+      h_args_->using_x = 0; h_args_->cplx = cplx; h_args_->skip_exact = 0; h_args_->nforms = (int)nforms; h_args_->best_match0 = 0;
+      h_args_->cap_nodes = (u32)std::min<size_t>(nodes_.cap, 0xffffffffu);
+      h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
+      h_args_->cap_events = (u32)events_.cap; h_args_->seq = 0;
+      h_args_->shard_rank = 0; h_args_->shard_world = 1; h_args_->gathered = 0; h_args_->shard_bound = 0;
+      h_args_->track_m = 1; h_args_->cap_tail = (u32)tail_.cap; h_args_->p_min = shared_->p_min;
+      CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc), cudaMemcpyHostToDevice, st_));
+      launch_stages(0, 0, max_len, 0, false);
+      CUDA_CHECK(cudaMemcpyAsync(&c, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      if (!c.overflow) break;
+      if (c.overflow & OVF_NODES) want_nodes = std::max<size_t>(nodes_.cap * 2, (size_t)c.node_count * 2);
+      if (c.overflow & OVF_DONE) want_done = std::max<size_t>(done_.cap * 2, (size_t)c.done_count * 2);
+      if (c.overflow & OVF_TAIL) want_tail = std::max<size_t>(tail_.cap * 2, (size_t)c.n_tail * 2);
+    }
+    SharedPass sp;
+    sp.n_slots = c.done_count; sp.n_tail = c.n_tail; sp.node_count = c.node_count; sp.dead_base = c.dead; sp.gen = c.gen;
+    CUDA_CHECK(cudaMalloc(&sp.rows, std::max<size_t>(sp.n_slots, 1) * sizeof(Row)));
+    CUDA_CHECK(cudaMalloc(&sp.forms, std::max<size_t>(sp.n_slots, 1) * sizeof(uint16_t)));
+    CUDA_CHECK(cudaMalloc(&sp.tail, std::max<size_t>(sp.n_tail, 1) * sizeof(TailRec)));
+    if (sp.n_slots) {
+      CUDA_CHECK(cudaMemcpyAsync(sp.rows, done_.p, (size_t)sp.n_slots * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(sp.forms, done_form_.p, (size_t)sp.n_slots * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
+    }
+    if (sp.n_tail) CUDA_CHECK(cudaMemcpyAsync(sp.tail, tail_.p, (size_t)sp.n_tail * sizeof(TailRec), cudaMemcpyDeviceToDevice, st_));
+    CUDA_CHECK(cudaMemcpyAsync(d_P_, &cur_P_, sizeof(RiesParams), cudaMemcpyHostToDevice, st_)); /* this target's own bound again */
+    CUDA_CHECK(cudaStreamSynchronize(st_)); /* other engines read the copy from their own streams */
+    shared_->passes.emplace(cplx, sp);
+    shared_->built++;
+    return sp;
+  }
+
+  /* Rows per rank in the exchange of the coming sharded pass: from what the largest rank kept in the side's last
+     sharded pass (same-side passes grow ~1.33x), or, for the first sharded pass of a side, from the keys of its
+     last unsharded one.  Too small is not wrong: the pass is rerun (OVF_KEPT). */
+  u32 shard_bound(int side, int world) {
+    size_t est = shard_kept_[side] ? (size_t)shard_kept_[side] * 17 / 10
+                                   : ((size_t)prev_keys_[side] * 2 / (size_t)world) * 3 / 2;
+    est = std::max<size_t>(est, 4096);
+    est = (est + 1023) & ~(size_t)1023;
+    return (u32)std::min<size_t>(est, 0x7fffffffu / (size_t)world);
+  }
+
+  /* Front half of a pass sharded over `world` ranks (or virtual ranks): K1 on this rank's forms, the hash
+     pre-dedupe into the send slot, the fixed-size all-gather of the slots, the totals into the control block
+     (shard.cuh).  Nothing here waits for the device: the overflow flags of all ranks arrive in the gathered
+     headers and end up in the control block the host reads at the end of the pass, so every rank takes the same
+     decision. */
+  void sharded_front(int max_len, int small, u32 bound, int world) {
     const DistState& ds = dist_state();
     const bool fake = ds.fake_world > 1;
-    const int world = fake ? ds.fake_world : ds.world;
-    std::vector<PassCtl> all((size_t)world);
     bool ch = false;
-    ch |= keep_.ensure(done_.cap, st_);
-    ch |= ksend_.ensure(done_.cap, st_);
-    ch |= ksend_form_.ensure(done_.cap, st_);
-    ch |= gdone_.ensure(1, st_);
-    ch |= gdone_form_.ensure(1, st_);
-    if (ch) { ptrs_dirty_ = true; upload_ptrs(); }
-    const u32 g_wide = small ? 12u : wide_grid_;
-    /* K1 -> keys (hash pre-dedupe) + sort of this rank's own expressions -> drop what cannot matter -> compact */
+    ch |= ksend_.ensure(bound, st_);
+    ch |= ksend_form_.ensure(bound, st_);
+    ch |= gdone_.ensure((size_t)world * bound, st_);
+    ch |= gdone_form_.ensure((size_t)world * bound, st_);
+    /* the replicated half sorts up to world x bound keys */
+    if ((size_t)world * bound > done_.cap) { grow_arena(nodes_.cap, (size_t)world * bound); ch = true; }
+    ensure_table((size_t)nt_ + (size_t)world * bound);
+    if (ch || ptrs_dirty_) { ptrs_dirty_ = true; upload_ptrs(); }
+    const u32 g_keys = small ? 12u : (u32)num_sms_ * 4;
     auto local_front = [&]() {
-      launch_stages(0, 1, max_len, small, true);
-      k_local_filter<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-      k_compact_kept<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
-      bump_epoch();
-      k_stage1_reset<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-      kernel_launches += 3;
-      stage_launches[1] += 3;
+      launch_stages(0, 0, max_len, small, false);
+      k_keys_send<<<g_keys, KK_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
+      k_send_hdr<<<1, 32, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
+      kernel_launches += 2;
+      stage_launches[1] += 2;
     };
     if (fake) {
-      /* test hook: the virtual ranks run one after the other on this GPU; the "all-gather" is a copy */
-      size_t off = 0;
-      u32 ovf = 0;
+      /* test hook: the virtual ranks run one after the other on this GPU; the "all-gather" is three copies */
       for (int r = 0; r < world; r++) {
+        CUDA_CHECK(cudaStreamSynchronize(st_)); /* the pinned arguments are about to change */
         h_args_->shard_rank = r;
         CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET, cudaMemcpyHostToDevice, st_));
         local_front();
-        CUDA_CHECK(cudaMemcpyAsync(h_ctl_, d_ctl_, sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        collect_stage_times(0, 1);
-        all[r] = *h_ctl_;
-        ovf |= h_ctl_->overflow;
-        if (h_ctl_->overflow) break;
-        const size_t c = h_ctl_->n_kept;
-        if (off + c > done_.cap) { ovf |= OVF_DONE; *want_done = std::max(*want_done, (off + c) * 2); break; }
-        if (gdone_.ensure(off + c, st_, true)) ptrs_dirty_ = true;
-        if (gdone_form_.ensure(off + c, st_, true)) ptrs_dirty_ = true;
-        if (c) {
-          CUDA_CHECK(cudaMemcpyAsync(gdone_.p + off, ksend_.p, c * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
-          CUDA_CHECK(cudaMemcpyAsync(gdone_form_.p + off, ksend_form_.p, c * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
-        }
-        off += c;
+        CUDA_CHECK(cudaMemcpyAsync(gdone_.p + (size_t)r * bound, ksend_.p, (size_t)bound * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(gdone_form_.p + (size_t)r * bound, ksend_form_.p, (size_t)bound * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(d_ghdr_ + r, d_shdr_, sizeof(SlotHdr), cudaMemcpyDeviceToDevice, st_));
       }
-      if (ovf) {
-        for (int r = 0; r < world; r++) {
-          if (all[r].overflow & OVF_NODES) *want_nodes = std::max(*want_nodes, (size_t)all[r].node_count * 2);
-          if (all[r].overflow & OVF_DONE) *want_done = std::max(*want_done, (size_t)all[r].done_count * 2);
-        }
-        return ovf;
-      }
+      CUDA_CHECK(cudaStreamSynchronize(st_));
     } else {
       local_front();
-      allctl_.ensure((size_t)world, st_); /* not in the pointer table */
-      dist_allgather(d_ctl_, allctl_.p, sizeof(PassCtl), st_);
-      CUDA_CHECK(cudaMemcpyAsync(h_allctl_, allctl_.p, (size_t)world * sizeof(PassCtl), cudaMemcpyDeviceToHost, st_));
-      CUDA_CHECK(cudaStreamSynchronize(st_));
-      collect_stage_times(0, 1);
-      d2h_bytes += (size_t)world * sizeof(PassCtl);
-      u32 ovf = 0;
-      size_t total = 0;
-      for (int r = 0; r < world; r++) {
-        all[r] = h_allctl_[r];
-        ovf |= all[r].overflow;
-        total += all[r].n_kept;
-        if (all[r].overflow & OVF_NODES) *want_nodes = std::max(*want_nodes, (size_t)all[r].node_count * 2);
-        if (all[r].overflow & OVF_DONE) *want_done = std::max(*want_done, (size_t)all[r].done_count * 2);
-      }
-      if (!ovf && total > done_.cap) { ovf |= OVF_DONE; *want_done = std::max(*want_done, total * 2); }
-      if (ovf) return ovf;
-      if (gdone_.ensure(total, st_)) ptrs_dirty_ = true;
-      if (gdone_form_.ensure(total, st_)) ptrs_dirty_ = true;
-      std::vector<size_t> bytes((size_t)world), offs((size_t)world);
-      size_t off = 0;
-      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].n_kept * sizeof(Row); offs[r] = off * sizeof(Row); off += all[r].n_kept; }
       CUDA_CHECK(cudaEventRecord(ev_g_[0], st_));
-      dist_allgatherv(ksend_.p, gdone_.p, bytes.data(), offs.data(), st_);
-      off = 0;
-      for (int r = 0; r < world; r++) { bytes[r] = (size_t)all[r].n_kept * sizeof(uint16_t); offs[r] = off * sizeof(uint16_t); off += all[r].n_kept; }
-      dist_allgatherv(ksend_form_.p, gdone_form_.p, bytes.data(), offs.data(), st_);
+      dist_allgather3(d_shdr_, d_ghdr_, sizeof(SlotHdr), ksend_.p, gdone_.p, (size_t)bound * sizeof(Row),
+                      ksend_form_.p, gdone_form_.p, (size_t)bound * sizeof(uint16_t), st_);
       CUDA_CHECK(cudaEventRecord(ev_g_[1], st_));
       gather_pending_ = true;
-      gather_bytes += total * (sizeof(Row) + sizeof(uint16_t));
     }
-    /* totals into the device control block, as if one K1 had produced exactly the kept expressions; from
-       here on the regroup kernels read the gathered arrays */
-    PassCtl t = all[0];
-    unsigned long long nodes = 0, done = 0, kept = 0, dead = 0;
-    for (int r = 0; r < world; r++) { nodes += all[r].node_count; done += all[r].gen; kept += all[r].n_kept; dead += all[r].dead; }
-    t.node_count = (u32)std::min<unsigned long long>(nodes, 0xffffffffull);
-    t.done_count = (u32)kept; /* the gathered rows have no holes */
-    t.gen = done;
-    t.dead = dead;
-    t.n_keys = 0;
-    t.lvl_begin = t.lvl_end = 0; t.tile_ticket = 0; t.blocks_done = 0; t.chunk_ticket = 0; t.aux_ticket = 0;
-    *gen_k1 = done;
-    *h_ctl_ = t;
-    CUDA_CHECK(cudaMemcpyAsync(d_ctl_, h_ctl_, sizeof(PassCtl), cudaMemcpyHostToDevice, st_));
-    h_args_->gathered = 1;
-    CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET, cudaMemcpyHostToDevice, st_));
-    if (ptrs_dirty_) upload_ptrs();
-    return 0;
+    /* from here on the kernels read the gathered slots (second copy of the pass's scalars: the first may not
+       have been consumed yet) */
+    memcpy(h_args2_, h_args_, sizeof(PassArgs));
+    h_args2_->gathered = 1;
+    CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_args2_, sizeof(PassArgs), cudaMemcpyHostToDevice, st_));
+    bump_epoch();
+    k_gather_hdr<<<1, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+    kernel_launches += 1;
+    stage_launches[1] += 1;
   }
 
   /* The hash sets restart small with every search and grow with the side's row count: at most half full after
@@ -831,7 +969,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
     DevPtrs& h = *h_ptrs_;
     h.P = d_P_; h.tt = d_tt_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
-    h.keep = keep_.p; h.ksend = ksend_.p; h.ksend_form = ksend_form_.p;
+    h.ksend = ksend_.p; h.ksend_form = ksend_form_.p; h.shdr = d_shdr_; h.ghdr = d_ghdr_; h.tail = tail_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.uniq_sk = uniq_sk_.p; h.events = events_.p; h.staged = staged_.p;
     for (int sd = 0; sd < 2; sd++) { h.hset[sd] = hset_[sd].p; h.hset_log2[sd] = hset_log2_[sd]; }
@@ -842,7 +980,7 @@ class DeviceEngine : public Engine {
   }
 
   cudaStream_t st_;
-  int num_sms_ = 0;
+  int num_sms_ = 0, dev_ = 0;
   u32 expand_grid_ = 0, wide_grid_ = 0;
   int k1_nq_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
@@ -885,15 +1023,20 @@ class DeviceEngine : public Engine {
   DevBuf<Row> done_, surv_, gdone_, ksend_;
   DevBuf<uint16_t> done_form_, gdone_form_, ksend_form_;
   DevBuf<SeqKey> uniq_sk_;
+  DevBuf<TailRec> tail_;
+  SharedRhs* shared_ = 0; /* the batch's RHS database, if this engine works for a sharing batch */
+  bool shared_ok_ = false;
+  RiesParams cur_P_;
   /* per side: hash set of the table's keys (state.cuh); rows that side holds, new rows of its last pass */
   DevBuf<u64> hset_[2];
   u32 hset_log2_[2] = {0, 0};
   size_t side_rows_[2] = {0, 0};
   u32 prev_new_[2] = {0, 0};
   bool last_tiny_ = false, last_using_x_ = false;
-  DevBuf<unsigned char> keep_;
-  DevBuf<PassCtl> allctl_;
-  PassCtl* h_allctl_ = 0; /* pinned, MAX_RANKS entries */
+  PassArgs* h_args2_ = 0; /* pinned: the scalars of a sharded pass's replicated half */
+  SlotHdr* d_shdr_ = 0;   /* this rank's send-slot header; the gathered headers (RIES_MAX_RANKS) */
+  SlotHdr* d_ghdr_ = 0;
+  u32 prev_gen_[2] = {0, 0}, prev_keys_[2] = {0, 0}, shard_kept_[2] = {0, 0};
   u32 shard_min_ = 100000; /* complete expressions in the previous same-side pass from which a pass is sharded */
   DevBuf<u64> rs_state_, cc_state_;
   DevBuf<Staged> staged_;

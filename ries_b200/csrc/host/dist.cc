@@ -112,20 +112,13 @@ void dist_allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStr
   check(g_api.AllGather(send, recv, bytes_per_rank, NCCL_INT8, (nccl_comm_t)g_dist.comm, st), "ncclAllGather");
 }
 
-void dist_allgatherv(const void* send, void* recv, const size_t* bytes, const size_t* offset, cudaStream_t st) {
-  /* every rank pushes its segment to every peer (one grouped send/recv: direct NVLink copies through the
-     switch, all pairs at once) and copies its own into place */
-  const int me = g_dist.rank;
-  if (bytes[me]) {
-    cudaError_t e = cudaMemcpyAsync((char*)recv + offset[me], send, bytes[me], cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) { fprintf(stderr, "ries_b200: gather copy failed: %s\n", cudaGetErrorString(e)); abort(); }
-  }
+void dist_allgather3(const void* s0, void* r0, size_t b0, const void* s1, void* r1, size_t b1, const void* s2, void* r2,
+                     size_t b2, cudaStream_t st) {
+  nccl_comm_t c = (nccl_comm_t)g_dist.comm;
   check(g_api.GroupStart(), "ncclGroupStart");
-  for (int d = 1; d < g_dist.world; d++) {
-    const int to = (me + d) % g_dist.world, from = (me - d + g_dist.world) % g_dist.world;
-    if (bytes[me]) check(g_api.Send(send, bytes[me], NCCL_INT8, to, (nccl_comm_t)g_dist.comm, st), "ncclSend");
-    if (bytes[from]) check(g_api.Recv((char*)recv + offset[from], bytes[from], NCCL_INT8, from, (nccl_comm_t)g_dist.comm, st), "ncclRecv");
-  }
+  check(g_api.AllGather(s0, r0, b0, NCCL_INT8, c, st), "ncclAllGather");
+  check(g_api.AllGather(s1, r1, b1, NCCL_INT8, c, st), "ncclAllGather");
+  check(g_api.AllGather(s2, r2, b2, NCCL_INT8, c, st), "ncclAllGather");
   check(g_api.GroupEnd(), "ncclGroupEnd");
 }
 

@@ -2,8 +2,8 @@
 //
 // north_star row (e): "the LHS index space shards across the GPUs of one box, the RHS table is generated
 // redundantly or all-gathered over NVLink with NCCL".  Here both sides shard the same way: the forms of a
-// large pass are dealt round-robin to the ranks for enumerate+evaluate (K1), the ranks' complete expressions
-// are all-gathered in rank-major order, and everything downstream runs replicated (see engine.cu).
+// large pass are dealt round-robin to the ranks for enumerate+evaluate (K1) and the hash pre-dedupe, what
+// survives is all-gathered in fixed-size slots, and everything downstream runs replicated (device/shard.cuh).
 //
 // NCCL is bound at run time (dlopen of the libnccl.so.2 already in the process, e.g. torch's), so the
 // single-GPU library and the `ries` binary have no NCCL dependency.
@@ -30,7 +30,8 @@ void dist_finalize();
 
 /* stream-ordered collectives over raw bytes */
 void dist_allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st);
-/* all-gather with per-rank sizes: rank r's `bytes[r]` bytes at `send` land at recv + offset[r] on every rank */
-void dist_allgatherv(const void* send, void* recv, const size_t* bytes, const size_t* offset, cudaStream_t st);
+/* three all-gathers as one NCCL group (headers, rows, form indices of a sharded pass) */
+void dist_allgather3(const void* s0, void* r0, size_t b0, const void* s1, void* r1, size_t b1, const void* s2, void* r2,
+                     size_t b2, cudaStream_t st);
 
 }  // namespace ries

@@ -137,7 +137,21 @@ class Engine {
      early-exit accounting */
   virtual long inserted_before(const MatchEvent& ev, bool inclusive) = 0;
   virtual const char* name() const = 0;
+  /* batch of targets sharing one enumeration of the right-hand sides (device engine only): the context made by
+     shared_rhs_create(), or 0 */
+  virtual void set_shared(void* ctx) { (void)ctx; }
 };
+
+/* One RHS database for a batch of targets (BASELINE config 5).  `sig` is the RiesParams all sharing targets have in
+   common (target-dependent fields cleared, see shared_rhs_signature), p_max / p_min the largest and smallest
+   overflow bound p_ovr among them.  The context owns device memory: destroy it after the batch, from any thread. */
+void* shared_rhs_create(const RiesParams& sig, double p_max, double p_min);
+void shared_rhs_destroy(void* ctx);
+void shared_rhs_stats(void* ctx, unsigned long long* passes_built, unsigned long long* consumer_passes);
+RiesParams shared_rhs_signature(const RiesParams& P);
+/* the search parameters a command line leads to, without searching (what ries_batch needs to plan the sharing);
+   false when the arguments do not describe a search */
+bool search_params(int argc, char** argv, RiesParams* out);
 
 struct RunStats {
   double lhs_gen = 0, rhs_gen = 0, gen_total = 0;

@@ -1001,6 +1001,24 @@ struct Search {
 
 }  // namespace
 
+static void null_sink_fn(void*, const char*, size_t) {}
+
+bool search_params(int argc, char** argv, RiesParams* outp) {
+  Sink sink{null_sink_fn, 0};
+  try {
+    Options opt;
+    parse_args(argc, argv, opt, sink);
+    if (opt.show_ss) return false;
+    Setup S;
+    build_setup(opt, S, sink);
+    finish_setup(opt, S, sink);
+    *outp = S.P;
+    return true;
+  } catch (const ExitRequest&) {
+    return false;
+  }
+}
+
 int run_search(Options& opt, Engine& eng, const Sink& out, RunStats* stats_out) {
   Search s(opt, eng, out);
   int code = 0;

@@ -16,7 +16,7 @@ def declared_functions():
 
 
 def test_header_declares_the_boundary():
-    assert declared_functions() == ["ries_batch", "ries_dist_finalize", "ries_dist_init", "ries_dist_unique_id",
+    assert declared_functions() == ["ries_batch", "ries_batch_shared_stats", "ries_dist_finalize", "ries_dist_init", "ries_dist_unique_id",
                                     "ries_engine_name", "ries_fp64_peak_tflops", "ries_last_stats", "ries_main"]
 
 
