@@ -321,7 +321,7 @@ def main():
                     help="search: one full-depth search per step (default); batch: BASELINE config 5 as the headline")
     ap.add_argument("--batch-size", type=int, default=256, help="targets over all ranks (batch object / workload)")
     ap.add_argument("--batch-level", default="4")
-    ap.add_argument("--workers", type=int, default=8, help="concurrent engines per GPU (batch)")
+    ap.add_argument("--workers", type=int, default=16, help="concurrent engines per GPU (batch)")
     ap.add_argument("--independent-targets", action="store_true",
                     help="N>1: one independent target per rank (weak scaling, no collective) instead of ONE search "
                          "over the N GPUs")

@@ -207,7 +207,7 @@ extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags
   }
   auto worker = [&]() {
     ries::Engine* eng = pool_take();
-    if (eng) eng->set_shared(shared);
+    if (eng) { eng->set_shared(shared); eng->set_throughput_mode(n_workers > 1); }
     while (true) {
       int i = next.fetch_add(1);
       if (i >= n_targets) break;
@@ -230,13 +230,13 @@ extern "C" int ries_batch(int n_targets, const char* const* targets, int n_flags
           if (code == 1 && opt.got_target) { /* out of device memory: do not reuse half-grown buffers */
             delete eng;
             eng = pool_take();
-            if (eng) eng->set_shared(shared);
+            if (eng) { eng->set_shared(shared); eng->set_throughput_mode(n_workers > 1); }
           }
         } catch (...) {
           code = 3;
           delete eng;
           eng = pool_take();
-          if (eng) eng->set_shared(shared);
+          if (eng) { eng->set_shared(shared); eng->set_throughput_mode(n_workers > 1); }
         }
       }
       if (code != 0 && code != RIES_EXIT_NO_ERROR) failures++;

@@ -142,7 +142,11 @@ struct SharedRhs {
   std::atomic<unsigned long long> built{0}, consumed{0};
   ~SharedRhs() {
     cudaSetDevice(dev);
-    for (auto& kv : passes) { cudaFree(kv.second.rows); cudaFree(kv.second.forms); cudaFree(kv.second.tail); }
+    for (auto& kv : passes) {
+      cudaFreeAsync(kv.second.rows, cudaStreamPerThread); cudaFreeAsync(kv.second.forms, cudaStreamPerThread);
+      cudaFreeAsync(kv.second.tail, cudaStreamPerThread);
+    }
+    cudaStreamSynchronize(cudaStreamPerThread);
   }
 };
 
@@ -271,6 +275,7 @@ class DeviceEngine : public Engine {
   }
   const char* name() const override { return "sm_100a"; }
   void set_shared(void* ctx) override { shared_ = static_cast<SharedRhs*>(ctx); }
+  void set_throughput_mode(bool on) override { throughput_mode_ = on && getenv("RIES_BATCH_FULL_GRIDS") == 0; }
 
   void begin(const RiesParams& P) override {
     /* the calling thread may be a new one (batch workers take pooled engines): its current device is 0 */
@@ -407,7 +412,14 @@ class DeviceEngine : public Engine {
       h_args_->cap_done = (u32)std::min<size_t>(done_.cap, 0xffffffffu);
       h_args_->cap_events = (u32)events_.cap; h_args_->seq = ++pass_seq_;
       /* size class from the previous pass of the same side (sizes grow ~1.3-1.6x per complexity step) */
-      const int small = (prev_nodes_[side] <= 12000 && prev_done_[side] <= 3000) ? 1 : 0;
+      int small = (prev_nodes_[side] <= 12000 && prev_done_[side] <= 3000) ? 1 : 0;
+      /* throughput mode (the engines of a batch share the GPU): a mid-size pass on full grids keeps the whole
+         machine busy scheduling blocks that find nothing to do, and K1's queues fill better when a block sees
+         several tiles; a lone search wants the latency of full grids instead */
+      if (!small && throughput_mode_ && nt_ <= 4000000u) {
+        if (prev_nodes_[side] <= 150000) small = 2;
+        else if (prev_nodes_[side] <= 1200000) small = 3;
+      }
       /* one search over several GPUs: only passes big enough to pay for the exchange are sharded */
       const DistState& ds = dist_state();
       const int shard_world = ds.fake_world > 1 ? ds.fake_world : ds.world;
@@ -445,8 +457,7 @@ class DeviceEngine : public Engine {
         CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                    cudaMemcpyHostToDevice, st_));
         if (host_prof_) hp_t1 = now_us();
-        launch_stages(4, 4, max_len, small, false); /* the shared front: control block, keys, sort */
-        launch_stages(2, 3, max_len, small, false);
+        launch_pass(1, max_len, small); /* the shared front (control block, keys, sort), then stages 2 and 3 */
         if (host_prof_) hp_t2 = now_us();
         wait_pass();
         if (host_prof_) hp_t3 = now_us();
@@ -461,7 +472,8 @@ class DeviceEngine : public Engine {
         collect_stamp_times();
       } else if (!shard) {
         if (host_prof_) hp_t1 = now_us();
-        launch_stages(0, 3, max_len, small, stage_events_);
+        if (stage_events_) launch_stages(0, 3, max_len, small, true);
+        else launch_pass(0, max_len, small);
         if (host_prof_) hp_t2 = now_us();
         wait_pass();
         if (stage_events_) CUDA_CHECK(cudaStreamSynchronize(st_)); /* the last event must have completed */
@@ -625,10 +637,13 @@ class DeviceEngine : public Engine {
     /* every kernel loops over its work (ticket / grid-stride), so the grid only sets the parallelism:
        the "small" variant is for passes predicted to be tiny, where launching a thousand blocks that
        exit at once costs more than the work itself.  A wrong prediction is slow, never wrong. */
-    const u32 g_exp = small ? 24u : expand_grid_;
-    const u32 g_wide = small ? 12u : wide_grid_;
-    const u32 g_keys = small ? 12u : (u32)num_sms_ * 4;
-    const u32 g_sort = small ? 12u : (u32)num_sms_ * RS_MIN_BLOCKS;
+    /* `small`: 0 full grids; 1 a pass predicted to be small; 2, 3 (throughput mode only, see run_pass): mid-size
+       passes on a sixteenth / a quarter of the machine */
+    const u32 div = small == 2 ? 16u : small == 3 ? 4u : 1u;
+    const u32 g_exp = small == 1 ? 24u : std::max(24u, expand_grid_ / div);
+    const u32 g_wide = small == 1 ? 12u : std::max(24u, wide_grid_ / div);
+    const u32 g_keys = small == 1 ? 12u : std::max(16u, (u32)num_sms_ * 4 / div);
+    const u32 g_sort = small == 1 ? 12u : std::max(12u, (u32)num_sms_ * RS_MIN_BLOCKS / div);
     switch (stage) {
       case 0:
         k_pass_begin<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
@@ -653,7 +668,7 @@ class DeviceEngine : public Engine {
       case 2:
         k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
         k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-        k_merge_old<<<small ? 48u : wide_grid_, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+        k_merge_old<<<small == 1 ? 48u : std::max(48u, wide_grid_ / div), MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
         break;
       case 3:
         k_refine<<<small ? 8 : 64, 64, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
@@ -684,6 +699,57 @@ class DeviceEngine : public Engine {
   /* Stages [first, last] of a pass on the stream.  Per-stage device time comes from the device clock stamps
      the kernels leave in the control block (collect_stamp_times); only sharded passes, whose stages are
      interleaved with the exchange, bracket them with CUDA events (ev_[k] before stage k and after the last). */
+  void count_stage(int stage, int max_len) {
+    const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1 : (stage == 1) ? 9 : (stage == 2) ? 3 : (stage == 3) ? 2 : 10;
+    kernel_launches += k;
+    if (stage == 4) { stage_launches[0] += 1; stage_launches[1] += 9; }
+    else stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
+  }
+
+  /* A whole pass as ONE graph launch (per-stage device times come from the kernels' clock stamps, so nothing has to
+     be recorded between the stages): kind 0 the general pass (stages 0-3), 1 the consumer of a shared RHS pass
+     (stages 4, 2, 3), 2 a tiny pass.  With the per-pass argument copy that is two driver calls per pass -- what
+     a batch of concurrent engines, which serialise on the driver, is bound by. */
+  void launch_pass(int kind, int max_len, int small) {
+    bump_epoch();
+    static const int seq0[] = {0, 1, 2, 3}, seq1[] = {4, 2, 3};
+    const int* seq = kind == 0 ? seq0 : seq1;
+    const int nseq = kind == 0 ? 4 : kind == 1 ? 3 : 0;
+    auto enqueue = [&]() {
+      if (kind == 2) {
+        k_tiny_front<<<1, TINY_THREADS, TINY_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, tiny_frontier_);
+        k_merge_old<<<48u, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+        k_refine_end<<<1, 128, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+      } else {
+        for (int i = 0; i < nseq; i++) enqueue_stage(seq[i], max_len, small);
+      }
+    };
+    if (!use_graphs_) {
+      enqueue();
+    } else {
+      const int key = 100000 + kind * 10000 + (kind == 0 ? max_len : 0) * 4 + small + (kind == 2 ? (int)(tiny_frontier_ & 0xfff) * 0 : 0);
+      auto it = graphs_.find(key);
+      if (it == graphs_.end()) {
+        cudaGraph_t g;
+        CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+        enqueue();
+        CUDA_CHECK(cudaStreamEndCapture(st_, &g));
+        cudaGraphExec_t ge;
+        CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+        CUDA_CHECK(cudaGraphDestroy(g));
+        it = graphs_.emplace(key, ge).first;
+      }
+      CUDA_CHECK(cudaGraphLaunch(it->second, st_));
+    }
+    if (kind == 2) {
+      kernel_launches += 3;
+      stage_launches[0] += 1; stage_launches[2] += 1; stage_launches[3] += 1;
+      tiny_passes++;
+    } else {
+      for (int i = 0; i < nseq; i++) count_stage(seq[i], max_len);
+    }
+  }
+
   void launch_stages(int first, int last, int max_len, int small, bool events = false) {
     if (first == 0 || first == 4) bump_epoch();
     if (events) CUDA_CHECK(cudaEventRecord(ev_[first], st_));
@@ -706,10 +772,7 @@ class DeviceEngine : public Engine {
         CUDA_CHECK(cudaGraphLaunch(it->second, st_));
       }
       if (events) CUDA_CHECK(cudaEventRecord(ev_[stage + 1], st_));
-      const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1 : (stage == 1) ? 9 : (stage == 2) ? 3 : (stage == 3) ? 2 : 10;
-      kernel_launches += k;
-      if (stage == 4) { stage_launches[0] += 1; stage_launches[1] += 9; }
-      else stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
+      count_stage(stage, max_len);
     }
   }
 
@@ -750,15 +813,7 @@ class DeviceEngine : public Engine {
   }
 
   /* A pass predicted tiny: three direct launches (tiny_pass.cuh). */
-  void launch_tiny() {
-    bump_epoch();
-    k_tiny_front<<<1, TINY_THREADS, TINY_DYN_SMEM, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, tiny_frontier_);
-    k_merge_old<<<48u, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
-    k_refine_end<<<1, 128, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-    kernel_launches += 3;
-    stage_launches[0] += 1; stage_launches[2] += 1; stage_launches[3] += 1;
-    tiny_passes++;
-  }
+  void launch_tiny() { launch_pass(2, 0, 0); }
 
   /* device time per stage of the pass just synchronised, from the stamps in the copied-back control block */
   void collect_stamp_times() {
@@ -831,9 +886,10 @@ class DeviceEngine : public Engine {
     }
     SharedPass sp;
     sp.n_slots = c.done_count; sp.n_tail = c.n_tail; sp.node_count = c.node_count; sp.dead_base = c.dead; sp.gen = c.gen;
-    CUDA_CHECK(cudaMalloc(&sp.rows, std::max<size_t>(sp.n_slots, 1) * sizeof(Row)));
-    CUDA_CHECK(cudaMalloc(&sp.forms, std::max<size_t>(sp.n_slots, 1) * sizeof(uint16_t)));
-    CUDA_CHECK(cudaMalloc(&sp.tail, std::max<size_t>(sp.n_tail, 1) * sizeof(TailRec)));
+    /* stream-ordered allocations: cudaMalloc / cudaFree would synchronise the whole device, i.e. every engine of the batch */
+    CUDA_CHECK(cudaMallocAsync(&sp.rows, std::max<size_t>(sp.n_slots, 1) * sizeof(Row), st_));
+    CUDA_CHECK(cudaMallocAsync(&sp.forms, std::max<size_t>(sp.n_slots, 1) * sizeof(uint16_t), st_));
+    CUDA_CHECK(cudaMallocAsync(&sp.tail, std::max<size_t>(sp.n_tail, 1) * sizeof(TailRec), st_));
     if (sp.n_slots) {
       CUDA_CHECK(cudaMemcpyAsync(sp.rows, done_.p, (size_t)sp.n_slots * sizeof(Row), cudaMemcpyDeviceToDevice, st_));
       CUDA_CHECK(cudaMemcpyAsync(sp.forms, done_form_.p, (size_t)sp.n_slots * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st_));
@@ -1025,7 +1081,7 @@ class DeviceEngine : public Engine {
   DevBuf<SeqKey> uniq_sk_;
   DevBuf<TailRec> tail_;
   SharedRhs* shared_ = 0; /* the batch's RHS database, if this engine works for a sharing batch */
-  bool shared_ok_ = false;
+  bool shared_ok_ = false, throughput_mode_ = false;
   RiesParams cur_P_;
   /* per side: hash set of the table's keys (state.cuh); rows that side holds, new rows of its last pass */
   DevBuf<u64> hset_[2];

@@ -140,6 +140,8 @@ class Engine {
   /* batch of targets sharing one enumeration of the right-hand sides (device engine only): the context made by
      shared_rhs_create(), or 0 */
   virtual void set_shared(void* ctx) { (void)ctx; }
+  /* several engines share the GPU (a batch): size the grids of mid-size passes by the work, not for latency */
+  virtual void set_throughput_mode(bool on) { (void)on; }
 };
 
 /* One RHS database for a batch of targets (BASELINE config 5).  `sig` is the RiesParams all sharing targets have in
