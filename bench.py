@@ -268,7 +268,7 @@ def batch_object(args, ries_b200, rank, world, dist, torch):
     64 reports are compared with the reference's (tests/golden/batch_l4.json, made by tools/make_batch_golden.py)."""
     from ries_b200.parallel import shard_targets
     level = args.batch_level
-    alltargets = targets_for(args.batch_size)
+    alltargets = targets_for(args.batch_size * world)  # --batch-size is per GPU (weak scaling: independent units)
     mine = shard_targets(alltargets, rank, world)
     flags = ["-l" + level, "-F3", "--no-slow-messages"]
     ries_b200.batch(mine[:max(2 * args.workers, 8)], flags, workers=args.workers)  # warm-up: engines, graphs
@@ -298,7 +298,7 @@ def batch_object(args, ries_b200, rank, world, dist, torch):
         exprs, nt, checked, same = t.tolist()
         wall = tm.item()
     return {"workload": "BASELINE config 5: %d targets U(0,10) 6dp seed %d, `ries <t> -l%s -F3`, %d engines per GPU, "
-                        "%d GPU(s)" % (args.batch_size, BATCH_SEED, level, args.workers, world),
+                        "%d GPU(s), one RHS enumeration per GPU shared by its targets" % (args.batch_size * world, BATCH_SEED, level, args.workers, world),
             "targets": int(nt), "seconds": wall, "targets_per_sec": nt / wall, "targets_per_sec_per_gpu": nt / wall / world,
             "expr_per_sec": exprs / wall, "reports_checked_against_reference": int(checked),
             "reports_identical": int(same), "shared_rhs": ries_b200.batch_shared_stats(),
@@ -319,7 +319,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="N=1: skip the side configs and the batch object")
     ap.add_argument("--workload", default="search", choices=["search", "batch"],
                     help="search: one full-depth search per step (default); batch: BASELINE config 5 as the headline")
-    ap.add_argument("--batch-size", type=int, default=256, help="targets over all ranks (batch object / workload)")
+    ap.add_argument("--batch-size", type=int, default=256, help="targets per GPU (batch object / workload)")
     ap.add_argument("--batch-level", default="4")
     ap.add_argument("--workers", type=int, default=16, help="concurrent engines per GPU (batch)")
     ap.add_argument("--independent-targets", action="store_true",
@@ -572,8 +572,8 @@ def main():
         "note": "K1 does ~14 algorithmic flop and ~10 integer tests per exec(): it is bound by instruction issue and latency, not by the fp64 pipe or HBM (profiles/); both fractions are given so the distance to either roof is explicit",
     }
 
-    mode = ("ONE search over %d GPUs: forms dealt round-robin for K1, hash pre-dedupe + local sort per rank, NCCL "
-            "all-gather of the kept rows, replicated merge; every rank prints the full report" % world)
+    mode = ("ONE search over %d GPUs: (form, first symbol) pairs dealt round-robin for K1 + hash pre-dedupe, fixed-size "
+            "NCCL all-gather of what survives, replicated sort/merge; every rank prints the full report" % world)
     line = {
         "metric": "expressions_evaluated_per_sec",
         "value": exprs_all / wall_all if wall_all > 0 else 0.0,

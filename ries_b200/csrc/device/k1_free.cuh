@@ -44,8 +44,13 @@ __device__ __forceinline__ void push_tail(TailRec* tail, u32 cap, PassCtl* ctl, 
 /* dynamic shared memory: nq queues of XF_CAP entries (u32: index of the prefix in the node arena) */
 __host__ __device__ inline size_t xf_dyn_smem(int nq) { return (size_t)nq * XF_CAP * sizeof(u32); }
 
-__global__ void __launch_bounds__(XF_THREADS, XF_MIN_BLOCKS)
-k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+/* PERSIST = false: one launch per expression position (the launches of a pass are chained by programmatic
+   dependent launch).  PERSIST = true (k_expand_all): ONE launch runs every position of the pass, the blocks meeting
+   at a grid barrier between positions -- for the small and mid-size passes, where a launch per position costs
+   more than the position (a pass of 1e5 prefixes: ~15 us per launch against ~4 us per barrier).  The grid must be
+   co-resident (cooperative launch, at most occupancy x SMs blocks). */
+template <bool PERSIST>
+__device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   u32* const s_ent = (u32*)s_dyn; /* [nq][XF_CAP] rings */
   __shared__ RiesParams P;
@@ -74,26 +79,37 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
     if (tid == 0) { s_dead = 0; s_gen = 0; s_alloc_tag = 0; }
     if (tid < RIES_MAX_SYMS) s_opcnt[tid] = 0;
     if (tid < XF_MAXQ) { s_tail[tid] = 0; s_head[0][tid] = 0; s_head[1][tid] = 0; }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!PERSIST) {
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
   }
   __syncthreads();
-  const u32 lvl_begin = ctl->lvl_begin, lvl_end = ctl->lvl_end;
-  const u32 n = lvl_end - lvl_begin;
-  const u32 ntiles = (n + XF_TILE - 1) / XF_TILE;
   const int using_x = Ap->using_x, cplx = Ap->cplx;
   const u32 cap_nodes = Ap->cap_nodes, cap_done = Ap->cap_done;
   /* shared RHS pass (SharedRhs, engine.cu): M rides in `der`; records for what depends on a target's bound */
   const bool track_m = Ap->track_m != 0;
   const double p_min = Ap->p_min;
   const u32 cap_tail = Ap->cap_tail;
+  const u32 shard_world = (u32)Ap->shard_world, shard_rank = (u32)Ap->shard_rank;
   /* queue of (complete, class, slot) = complete * nsq + qoff[class] + slot; symbol of queue q = sym_of_q */
   const u32 qoff1 = (u32)P.cls_n[0], qoff2 = qoff1 + (u32)P.cls_n[1], nsq = qoff2 + (u32)P.cls_n[2];
   const u32 nq = 2 * nsq;
-  if (ntiles != 0 && !(ctl->overflow & (OVF_NODES | OVF_DONE))) {
-    Node* nodes = D.nodes;
-    const FormDesc* __restrict__ forms = D.forms;
-    u32 my_dead = 0, my_gen = 0;
+  Node* nodes = D.nodes;
+  const FormDesc* __restrict__ forms = D.forms;
+  u32 my_dead = 0, my_gen = 0;
+  const u32 bar_gen0 = PERSIST ? *(volatile u32*)&ctl->bar_gen : 0u;
+  for (u32 lvl = 0; lvl == 0 || (PERSIST && lvl <= RIES_MAX_ELEN); lvl++) {
+  if (PERSIST && lvl) { /* the queues and the hand-off word start every position empty */
+    if (tid == 0) s_alloc_tag = 0;
+    if (tid < XF_MAXQ) { s_tail[tid] = 0; s_head[0][tid] = 0; s_head[1][tid] = 0; }
+    __syncthreads();
+  }
+  const u32 lvl_begin = *(volatile u32*)&ctl->lvl_begin, lvl_end = *(volatile u32*)&ctl->lvl_end;
+  const u32 n = lvl_end - lvl_begin;
+  const u32 ntiles = (n + XF_TILE - 1) / XF_TILE;
+  if (PERSIST && ntiles == 0) break; /* uniform over the grid: every block reads the same bounds after the barrier */
+  if (ntiles != 0 && !(*(volatile u32*)&ctl->overflow & (OVF_NODES | OVF_DONE))) {
     bool draining = false;
     for (u32 par2 = 0; !draining; par2 ^= 1u) {
       /* the batch cursor and the queue heads alternate between two copies: there is no barrier at the end of a
@@ -114,9 +130,20 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
             const int ns = P.cls_n[cls];
             const int atts = prefix_attrs(P, F, par, using_x);
             u32 mask = expand_mask(P, TT, F, par, cls, atts, using_x, cplx, cplx);
-            my_dead += (u32)ns - (u32)__popc(mask);
-            if (track_m && par.der >= p_min && (u32)ns != (u32)__popc(mask)) /* gone with the prefix, for a smaller bound */
-              push_tail(D.tail, cap_tail, ctl, -1.0 / 0.0, par.der, -(int)((u32)ns - (u32)__popc(mask)));
+            u32 rejected = (u32)ns - (u32)__popc(mask);
+            if (shard_world > 1 && par.len == 0) {
+              /* one search over several GPUs: rank r enumerates the (form, first symbol) pairs with
+                 (13 form + slot) mod world == r -- finer than whole forms, whose sizes differ by orders of
+                 magnitude; a rejected first symbol is a dead-end of the rank that owns the pair */
+              u32 own = 0;
+              for (int k = 0; k < ns; k++)
+                if ((13u * (u32)par.form + (u32)k) % shard_world == shard_rank) own |= 1u << k;
+              rejected = (u32)__popc(own & ~mask);
+              mask &= own;
+            }
+            my_dead += rejected;
+            if (track_m && par.der >= p_min && rejected) /* gone with the prefix, for a smaller bound */
+              push_tail(D.tail, cap_tail, ctl, -1.0 / 0.0, par.der, -(int)rejected);
             const u32 q0 = ((par.len + 1 >= F.flen) ? nsq : 0u) + (cls == 0 ? 0u : cls == 1 ? qoff1 : qoff2);
             while (mask) {
               const u32 k = (u32)__ffs((int)mask) - 1;
@@ -253,33 +280,47 @@ k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCt
         }
       }
     }
-    /* block-level counters -> one atomic each per block */
-    for (int o = 16; o > 0; o >>= 1) {
-      my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
-      my_gen += __shfl_xor_sync(0xffffffffu, my_gen, o);
-    }
-    if (lane == 0) { if (my_dead) atomicAdd(&s_dead, my_dead); if (my_gen) atomicAdd(&s_gen, my_gen); }
-    __syncthreads();
-    if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
-    if (tid == 0 && s_gen) atomicAdd(&ctl->gen, (u64)s_gen);
-    if (tid < RIES_MAX_SYMS && s_opcnt[tid]) atomicAdd(&D.opcnt[(using_x ? RIES_MAX_SYMS : 0) + tid], (u64)s_opcnt[tid]);
   }
-  /* ---- level finish by the last block to get here (replaces a separate launch) ---- */
+  /* ---- level finish by the last block to get here (replaces a separate launch); PERSIST: the others wait for it ---- */
   __syncthreads();
   if (tid == 0) {
     __threadfence();
     s_last = (atomicAdd(&ctl->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) {
+      __threadfence();
+      const u32 ovf = *(volatile u32*)&ctl->overflow;
+      const u32 alloc = *(volatile u32*)&ctl->node_count;
+      ctl->lvl_begin = lvl_end;
+      /* on overflow stop expanding: the host grows the arenas and reruns the pass */
+      ctl->lvl_end = (ovf & (OVF_NODES | OVF_DONE)) ? lvl_end : alloc;
+      ctl->tile_ticket = 0;
+      ctl->blocks_done = 0;
+      if (PERSIST) { __threadfence(); *(volatile u32*)&ctl->bar_gen = bar_gen0 + lvl + 1u; }
+    } else if (PERSIST) {
+      while (*(volatile u32*)&ctl->bar_gen != bar_gen0 + lvl + 1u) {}
+      __threadfence();
+    }
   }
   __syncthreads();
-  if (!s_last) return;
-  if (tid == 0) {
-    __threadfence();
-    const u32 ovf = *(volatile u32*)&ctl->overflow;
-    const u32 alloc = *(volatile u32*)&ctl->node_count;
-    ctl->lvl_begin = lvl_end;
-    /* on overflow stop expanding: the host grows the arenas and reruns the pass */
-    ctl->lvl_end = (ovf & (OVF_NODES | OVF_DONE)) ? lvl_end : alloc;
-    ctl->tile_ticket = 0;
-    ctl->blocks_done = 0;
+  } /* positions */
+  /* block-level counters -> one atomic each per block */
+  for (int o = 16; o > 0; o >>= 1) {
+    my_dead += __shfl_xor_sync(0xffffffffu, my_dead, o);
+    my_gen += __shfl_xor_sync(0xffffffffu, my_gen, o);
   }
+  if (lane == 0) { if (my_dead) atomicAdd(&s_dead, my_dead); if (my_gen) atomicAdd(&s_gen, my_gen); }
+  __syncthreads();
+  if (tid == 0 && s_dead) atomicAdd(&ctl->dead, (u64)s_dead);
+  if (tid == 0 && s_gen) atomicAdd(&ctl->gen, (u64)s_gen);
+  if (tid < RIES_MAX_SYMS && s_opcnt[tid]) atomicAdd(&D.opcnt[(using_x ? RIES_MAX_SYMS : 0) + tid], (u64)s_opcnt[tid]);
+}
+
+__global__ void __launch_bounds__(XF_THREADS, XF_MIN_BLOCKS)
+k_expand(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+  expand_body<false>(Dp, Ap, ctl);
+}
+
+__global__ void __launch_bounds__(XF_THREADS, XF_MIN_BLOCKS)
+k_expand_all(const DevPtrs* __restrict__ Dp, const PassArgs* __restrict__ Ap, PassCtl* ctl) {
+  expand_body<true>(Dp, Ap, ctl);
 }

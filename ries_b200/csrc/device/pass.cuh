@@ -6,12 +6,13 @@
 
 __device__ __forceinline__ void pass_begin_body(const DevPtrs* D, const PassArgs* A, PassCtl* C, TableState* T) {
   const u32 nforms = (u32)A->nforms;
-  const u32 world = (u32)A->shard_world, rank = (u32)A->shard_rank;
-  const u32 nroots = (nforms > rank) ? (nforms - rank + world - 1) / world : 0; /* forms dealt round-robin */
+  /* one search over several GPUs: every rank starts from all the forms; the unit dealt to the ranks is (form, first
+     symbol), at the first expression position (k1_free.cuh) */
+  const u32 nroots = nforms;
   for (u32 j = threadIdx.x; j < nroots; j += blockDim.x) {
     Node r;
     r.val = 0; r.der = 0; r.sym.lo = 0; r.sym.hi = 0;
-    r.below = RIES_NO_NODE; r.form = (uint16_t)(rank + j * world); r.cplx = 0; r.tag = 0; r.len = 0; r.sp = 0;
+    r.below = RIES_NO_NODE; r.form = (uint16_t)j; r.cplx = 0; r.tag = 0; r.len = 0; r.sp = 0;
     r.pad0 = 0; r.pad1 = 0;
     D->nodes[j] = r;
   }

@@ -80,7 +80,8 @@ struct PassCtl {
   u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
   u64 gen;                /* complete expressions generated (g_ne, ries.c:9190): done_count counts SLOTS, holes included */
   u32 max_nodes, max_done; /* sharded passes: the largest rank's node and expression slots (arena sizing) */
-  u32 n_tail, pad_tail;    /* TailRec records written (may exceed the capacity: then OVF_TAIL is set) */
+  u32 n_tail;              /* TailRec records written (may exceed the capacity: then OVF_TAIL is set) */
+  u32 bar_gen;             /* k_expand_all: grid-barrier generation (monotonic, survives passes) */
   /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] regroup +
      sort, [2] classify/match/merge, [3] refine, [4] end.  Written by thread 0 of block 0 of the stage's first
      kernel (the kernels of a pass run back to back on one stream), read by the host from the copied-back

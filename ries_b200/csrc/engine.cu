@@ -198,6 +198,12 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_DYN_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xf_dyn_smem(XF_MAXQ)));
     CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xf_dyn_smem(XF_MAXQ)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand_all, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    /* measured (tools/ab_l6.py, -l6 and the default level): no faster than the chained launches -- a small
+       position costs its dependent-load chain and two block barriers, not its launch -- so it stays an option */
+    use_persist_ = getenv("RIES_PERSIST") != 0;
+    if (const char* e = getenv("RIES_PERSIST_MAX")) persist_max_ = (u32)strtoul(e, 0, 10);
     (void)occ;
     wide_grid_ = (u32)(num_sms_ * 8);
     use_graphs_ = getenv("RIES_NO_GRAPHS") == 0;
@@ -319,7 +325,7 @@ class DeviceEngine : public Engine {
         graphs_.clear();
         k1_nq_ = nq;
         int occ = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand, XF_THREADS, xf_dyn_smem(nq)));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand_all, XF_THREADS, xf_dyn_smem(nq)));
         if (occ < 1) occ = 1;
         expand_grid_ = (u32)(num_sms_ * occ);
       }
@@ -438,6 +444,9 @@ class DeviceEngine : public Engine {
       CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_passin_, PASSIN_FORMS_OFFSET + nforms * sizeof(FormDesc),
                                  cudaMemcpyHostToDevice, st_));
       was_tiny = tiny;
+      /* small and mid-size passes: every expression position in ONE launch with grid barriers (k_expand_all); a
+         lone search only -- the barrier needs the whole grid resident, which engines sharing the GPU cannot promise */
+      persist_ = use_persist_ && !throughput_mode_ && !shard && prev_nodes_[side] <= persist_max_;
       const bool use_shared = !tiny && !shard && shared_wanted(using_x, cplx, side);
       was_shared = use_shared;
       if (use_shared) {
@@ -647,6 +656,18 @@ class DeviceEngine : public Engine {
     switch (stage) {
       case 0:
         k_pass_begin<<<1, 1024, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+        if (persist_) { /* every expression position in one cooperative launch (k_expand_all) */
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(std::min(g_exp, expand_grid_)); cfg.blockDim = dim3(XF_THREADS);
+          cfg.dynamicSmemBytes = xf_dyn_smem(k1_nq_); cfg.stream = st_;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeCooperative;
+          at[0].val.cooperative = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          const DevPtrs* a0 = d_ptrs_; const PassArgs* a1 = d_args_; PassCtl* a2 = d_ctl_;
+          CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_expand_all, a0, a1, a2));
+          break;
+        }
         for (int lvl = 0; lvl < max_len; lvl++) {
           /* positions after the first may overlap their prologue with the previous position's tail
              (programmatic dependent launch; the kernel waits on the dependency itself) */
@@ -700,7 +721,7 @@ class DeviceEngine : public Engine {
      the kernels leave in the control block (collect_stamp_times); only sharded passes, whose stages are
      interleaved with the exchange, bracket them with CUDA events (ev_[k] before stage k and after the last). */
   void count_stage(int stage, int max_len) {
-    const unsigned long long k = (stage == 0) ? (unsigned long long)max_len + 1 : (stage == 1) ? 9 : (stage == 2) ? 3 : (stage == 3) ? 2 : 10;
+    const unsigned long long k = (stage == 0) ? (persist_ ? 2ull : (unsigned long long)max_len + 1) : (stage == 1) ? 9 : (stage == 2) ? 3 : (stage == 3) ? 2 : 10;
     kernel_launches += k;
     if (stage == 4) { stage_launches[0] += 1; stage_launches[1] += 9; }
     else stage_launches[stage] += (stage == 0) ? k - 1 : k; /* stage 0: the K1 launches, not k_pass_begin */
@@ -727,7 +748,7 @@ class DeviceEngine : public Engine {
     if (!use_graphs_) {
       enqueue();
     } else {
-      const int key = 100000 + kind * 10000 + (kind == 0 ? max_len : 0) * 4 + small + (kind == 2 ? (int)(tiny_frontier_ & 0xfff) * 0 : 0);
+      const int key = 100000 + kind * 10000 + (kind == 0 ? (persist_ ? 30 : max_len) : 0) * 4 + small;
       auto it = graphs_.find(key);
       if (it == graphs_.end()) {
         cudaGraph_t g;
@@ -757,7 +778,7 @@ class DeviceEngine : public Engine {
       if (!use_graphs_) {
         enqueue_stage(stage, max_len, small);
       } else {
-        const int key = ((stage == 0) ? max_len : -stage) * 4 + small + 1000;
+        const int key = ((stage == 0) ? (persist_ ? 30 : max_len) : -stage) * 4 + small + 1000;
         auto it = graphs_.find(key);
         if (it == graphs_.end()) {
           cudaGraph_t g;
@@ -906,7 +927,7 @@ class DeviceEngine : public Engine {
      sharded pass (same-side passes grow ~1.33x), or, for the first sharded pass of a side, from the keys of its
      last unsharded one.  Too small is not wrong: the pass is rerun (OVF_KEPT). */
   u32 shard_bound(int side, int world) {
-    size_t est = shard_kept_[side] ? (size_t)shard_kept_[side] * 17 / 10
+    size_t est = shard_kept_[side] ? (size_t)shard_kept_[side] * 3 / 2
                                    : ((size_t)prev_keys_[side] * 2 / (size_t)world) * 3 / 2;
     est = std::max<size_t>(est, 4096);
     est = (est + 1023) & ~(size_t)1023;
@@ -1082,6 +1103,8 @@ class DeviceEngine : public Engine {
   DevBuf<TailRec> tail_;
   SharedRhs* shared_ = 0; /* the batch's RHS database, if this engine works for a sharing batch */
   bool shared_ok_ = false, throughput_mode_ = false;
+  bool use_persist_ = false, persist_ = false;
+  u32 persist_max_ = 3000000;
   RiesParams cur_P_;
   /* per side: hash set of the table's keys (state.cuh); rows that side holds, new rows of its last pass */
   DevBuf<u64> hset_[2];
