@@ -3,6 +3,13 @@
 usage: ncu_source_hot.py report.ncu-rep [top_n]"""
 import csv, subprocess, sys, collections
 
+def num(x):
+    try:
+        return int(x)
+    except (TypeError, ValueError):
+        return 0
+
+
 def main():
     rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
@@ -18,22 +25,22 @@ def main():
         d = dict(zip(hdr, r))
         # duplicate column name "Source": take by position
         rows.append((cur, int(r[0]), r[1].strip(), d))
-    tot_s = sum(int(d["# Samples"]) for _, _, _, d in rows) or 1
-    tot_i = sum(int(d["Instructions Executed"]) for _, _, _, d in rows) or 1
+    tot_s = sum(num(d["# Samples"]) for _, _, _, d in rows) or 1
+    tot_i = sum(num(d["Instructions Executed"]) for _, _, _, d in rows) or 1
     per_file = collections.Counter()
-    for f, _, _, d in rows: per_file[f] += int(d["# Samples"])
+    for f, _, _, d in rows: per_file[f] += num(d["# Samples"])
     print("samples per file:", {k: "%.1f%%" % (100.0 * v / tot_s) for k, v in per_file.most_common()})
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     st_tot = collections.Counter()
     for _, _, _, d in rows:
-        for s in stalls: st_tot[s] += int(d[s])
+        for s in stalls: st_tot[s] += num(d[s])
     print("stall mix:", {k: "%.1f%%" % (100.0 * v / tot_s) for k, v in st_tot.most_common(8)})
-    rows.sort(key=lambda x: -int(x[3]["# Samples"]))
+    rows.sort(key=lambda x: -num(x[3]["# Samples"]))
     print("%-14s %5s %7s %7s %5s  %-28s %s" % ("file", "line", "smp%", "inst%", "thr", "top stalls", "source"))
     for f, ln, src, d in rows[:top]:
-        s = int(d["# Samples"])
-        ts = sorted(((int(d[k]), k[6:]) for k in stalls), reverse=True)[:2]
-        print("%-14s %5d %6.2f%% %6.2f%% %5s  %-28s %s" % (f, ln, 100.0 * s / tot_s, 100.0 * int(d["Instructions Executed"]) / tot_i,
+        s = num(d["# Samples"])
+        ts = sorted(((num(d[k]), k[6:]) for k in stalls), reverse=True)[:2]
+        print("%-14s %5d %6.2f%% %6.2f%% %5s  %-28s %s" % (f, ln, 100.0 * s / tot_s, 100.0 * num(d["Instructions Executed"]) / tot_i,
               d["Avg. Threads Executed"], ",".join("%s:%d" % (k, v) for v, k in ts if v), src[:90]))
 
 main()
