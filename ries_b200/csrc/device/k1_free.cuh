@@ -59,7 +59,7 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
   __shared__ u32 s_head[2][XF_MAXQ]; /* entries ever taken off, by round parity (read-only during a round) */
   __shared__ u32 s_cum[XF_MAXQ + 1]; /* this round: first batch of queue q in the round's batch list */
   __shared__ u32 s_opcnt[RIES_MAX_SYMS];
-  __shared__ u32 s_tile, s_next[2], s_dead, s_gen, s_last;
+  __shared__ u32 s_tile, s_next[2], s_dead, s_gen, s_last, s_drain;
   __shared__ volatile u32 s_node_base, s_done_base;
   __shared__ volatile u32 s_alloc_tag;
   const u32 tid = threadIdx.x, lane = tid & 31;
@@ -97,6 +97,9 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
   const u32 nq = 2 * nsq;
   Node* nodes = D.nodes;
   const FormDesc* __restrict__ forms = D.forms;
+  Row* const done_rows = D.done;
+  uint16_t* const done_forms = D.done_form;
+  ASSUME_GLOBAL(nodes); ASSUME_GLOBAL(forms); ASSUME_GLOBAL(done_rows); ASSUME_GLOBAL(done_forms); ASSUME_GLOBAL(ctl);
   u32 my_dead = 0, my_gen = 0;
   const u32 bar_gen0 = PERSIST ? *(volatile u32*)&ctl->bar_gen : 0u;
   for (u32 lvl = 0; lvl == 0 || (PERSIST && lvl <= RIES_MAX_ELEN); lvl++) {
@@ -118,9 +121,9 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
       if (tid == 0) { s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next[par2] = 0; }
       __syncthreads(); /* also: every warp has left phase C of the previous round (queue entries may be overwritten) */
       const u32 tile = s_tile;
-      draining = tile >= ntiles; /* no tile left for this block: one last round takes everything off the queues */
+      const bool have_tile = tile < ntiles;
       /* ---- phase P ---- */
-      if (!draining) {
+      if (have_tile) {
         const u32 p = lvl_begin + tile * XF_TILE + tid;
         if (p < lvl_end) {
           const Node par = nodes[p];
@@ -154,7 +157,16 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
           }
         }
       }
+      /* the block's LAST round takes everything off the queues: when it got no tile, or when the tile it just got
+         was the last one anybody will get (the ticket counter has run past the end) -- which for a small position,
+         where a block sees one tile at most, saves the whole extra round */
+#ifdef XF_NO_DRAIN_FUSION
+      if (tid == 0) s_drain = have_tile ? 0u : 1u;
+#else
+      if (tid == 0) s_drain = (!have_tile || *(volatile u32*)&ctl->tile_ticket >= ntiles) ? 1u : 0u;
+#endif
       __syncthreads();
+      draining = s_drain != 0;
       /* ---- the round's batch list: queue q contributes its full batches (everything when draining) ---- */
       const u32* head = s_head[par2];
       u32 nb_total, nb_live; /* batches of the round; of which from the queues of incomplete prefixes */
@@ -270,10 +282,10 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
             if (oc == OUT_DONE) {
               expand_finish(P, par, g, child);
               Row r; r.val = child.val; r.der = child.der; r.sym = child.sym;
-              D.done[pos] = r;
-              D.done_form[pos] = child.form;
+              done_rows[pos] = r;
+              done_forms[pos] = child.form;
             } else {
-              D.done_form[pos] = (uint16_t)FORM_HOLE;
+              done_forms[pos] = (uint16_t)FORM_HOLE;
             }
           }
           if (oc == OUT_DONE) my_gen++;

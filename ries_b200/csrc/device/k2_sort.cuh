@@ -42,6 +42,7 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
   const SlotHdr* __restrict__ ghdr = D.ghdr;
   u64* keys = D.keys[0];
   u32* idx = D.idx[0];
+  ASSUME_GLOBAL(done); ASSUME_GLOBAL(done_form); ASSUME_GLOBAL(hs); ASSUME_GLOBAL(keys); ASSUME_GLOBAL(idx); ASSUME_GLOBAL(ghdr);
   for (int d = 0; d < 8; d++) s_h[d][tid] = 0;
   __syncthreads();
   for (u32 base = blockIdx.x * KK_CHUNK; base < n; base += gridDim.x * KK_CHUNK) {
@@ -237,6 +238,8 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
   u32* idx_out = Dp->idx[src ^ 1];
   SortCtl* ctl = Dp->sortctl;
   volatile u64* state = (volatile u64*)Dp->rs_state;
+  ASSUME_GLOBAL(keys_in); ASSUME_GLOBAL(idx_in); ASSUME_GLOBAL(keys_out); ASSUME_GLOBAL(idx_out); ASSUME_GLOBAL(ctl);
+  ASSUME_GLOBAL((const u64*)state);
   const u64 epoch = (u64)(T->epoch + (u32)pass);
   /* exclusive scan of the digit's global histogram: bin `tid` starts at gbase */
   u32 gbase;

@@ -86,6 +86,11 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   const uint16_t* __restrict__ surv_form = A->gathered ? D.gdone_form : D.done_form;
   const int using_x = A->using_x, skip_exact = A->skip_exact;
   volatile u64* state = (volatile u64*)D.cc_state;
+  u32* const uniq_seq_o = D.uniq_seq;
+  u32* const uniq_gap_o = D.uniq_gap;
+  SeqKey* const uniq_sk_o = D.uniq_sk;
+  ASSUME_GLOBAL(tval); ASSUME_GLOBAL(trow); ASSUME_GLOBAL(keys); ASSUME_GLOBAL(idx); ASSUME_GLOBAL(surv); ASSUME_GLOBAL(surv_form);
+  ASSUME_GLOBAL(uniq_seq_o); ASSUME_GLOBAL(uniq_gap_o); ASSUME_GLOBAL(uniq_sk_o); ASSUME_GLOBAL((const u64*)state);
   const u64 epoch = (u64)(T->epoch + 8u);
   while (true) {
     if (tid == 0) s_chunk = atomicAdd(&C->chunk_ticket, 1u);
@@ -219,12 +224,12 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
       const u32 b = __ballot_sync(0xffffffffu, fl);
       if (fl) {
         const u32 u = cbase + s_cnt[r * (CC_THREADS / 32) + warp] + __popc(b & ((1u << lane) - 1));
-        D.uniq_seq[u] = sq[r];
-        D.uniq_gap[u] = pos[r];
+        uniq_seq_o[u] = sq[r];
+        uniq_gap_o[u] = pos[r];
         SeqKey sk;
         const Sym128 sy = surv[sq[r]].sym;
         sk.lo = sy.lo; sk.hi = sy.hi; sk.form = surv_form[sq[r]]; sk.pad = 0;
-        D.uniq_sk[u] = sk;
+        uniq_sk_o[u] = sk;
       }
     }
     __syncthreads();
@@ -252,6 +257,8 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
   const double best_match0 = A->best_match0;
   u64* hs = Dp->hset[using_x ? 1 : 0];
   const u32 hlog = Dp->hset_log2[using_x ? 1 : 0];
+  ASSUME_GLOBAL(trow); ASSUME_GLOBAL(mrow); ASSUME_GLOBAL(mval); ASSUME_GLOBAL(uniq_seq); ASSUME_GLOBAL(uniq_gap);
+  ASSUME_GLOBAL(uniq_sk); ASSUME_GLOBAL(surv); ASSUME_GLOBAL(hs);
   for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
     const u32 g = uniq_gap[u];
     const Row f = surv[uniq_seq[u]];

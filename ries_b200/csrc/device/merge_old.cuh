@@ -39,6 +39,7 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
   Row* mrow = D.trow[T->cur ^ 1];
   double* mval = D.tval[T->cur ^ 1];
   const u32* __restrict__ uniq_gap = D.uniq_gap;
+  ASSUME_GLOBAL(trow); ASSUME_GLOBAL(mrow); ASSUME_GLOBAL(mval); ASSUME_GLOBAL(uniq_gap);
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   (void)lane;
   const u32 nchunks = (nt + MO_CHUNK - 1) / MO_CHUNK;

@@ -159,6 +159,14 @@ __device__ __forceinline__ bool seq_before(const SeqKey& a, const SeqKey& b) {
   return sym_before(a.lo, a.hi, b.lo, b.hi);
 }
 
+/* The buffer pointers come out of the device-resident pointer table, so the compiler cannot see their address
+   space and would emit generic loads and stores; every one of them is global memory. */
+#ifdef RIES_NO_ASSUME_GLOBAL
+#define ASSUME_GLOBAL(p) ((void)0)
+#else
+#define ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#endif
+
 #define FORM_HOLE 0xffffu /* done_form[] / Node::form of a slot that was allocated but not filled */
 
 /* Hash set of table keys, one per side: 4-slot buckets of 32 bytes (one DRAM sector per probe).  It only has to be

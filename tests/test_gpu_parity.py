@@ -93,7 +93,7 @@ def test_gpu_candidate_buffer_regrow(product_lib):
     exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
     for name in ("t25063_l3_F3_x", "i143_l3"):
         case = [c for c in golden_cases() if c["name"] == name][0]
-        r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+        r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True, timeout=180)
         assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(name)
 
 
@@ -103,7 +103,7 @@ def test_gpu_node_arena_regrow(product_lib):
     env = dict(os.environ, HOME="/nonexistent", RIES_ARENA_CAP="4096")
     exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
     case = [c for c in golden_cases() if c["name"] == "t25063_l3_F3_x"][0]
-    r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+    r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True, timeout=180)
     assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(case["name"])
 
 
@@ -135,7 +135,7 @@ def test_gpu_pass_variants_agree(product_lib, env_extra):
     exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
     for name in ("t25063_l3_F3_x", "i143_l3", "neg_l2"):
         case = [c for c in golden_cases() if c["name"] == name][0]
-        r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True)
+        r = subprocess.run([exe] + case["args"] + ["--no-slow-messages"], env=env, capture_output=True, text=True, timeout=180)
         assert normalise(r.stdout, exe) + "exit=%d\n" % r.returncode == golden_text(name)
 
 
@@ -159,6 +159,37 @@ def test_gpu_batch_of_targets_matches_reference(product_lib):
     # and the same batch again gives the same bytes (engines are reused, streams interleave differently)
     again = ries_b200.batch(targets[:24], flags, workers=5)
     assert [normalise(a[1]) for a in again] == [normalise(x[1]) for x in got[:24]]
+
+
+@pytest.mark.parametrize("flags,targets", [
+    # overflow bounds spread over four decades: every target's dead-end count is the shared one corrected by the
+    # recorded cases where ITS bound cuts in; 0.000731 is below the sharing floor and searches on its own
+    (["-l3", "-F3"], ["9876.54321", "431.7", "12.5", "2.5063", "1.0172", "0.93", "1.618034", "0.000731", "57.29578", "3.3"]),
+    # signs, an integer target (its class differs: x carries another tag), exact matches across sides
+    (["-l2", "-F0"], ["-1.234", "143", "2.5", "-7", "0.5", "6.283185", "1", "4.4934"]),
+    # restricted symbol sets change queues, rule masks and the -O counts; -i is demoted to -r for non-integers, which
+    # changes the parameters of those targets (they fall out of the sharing group)
+    (["-l3", "-S1234+-*/x", "-F3"], ["2.5063", "17", "0.75", "5.5", "1.3333"]),
+    (["-l2", "-i", "-F3"], ["143", "17", "2.5063", "64", "3.75"]),
+    (["-l2", "-NSCT", "-Op", "-x", "-F3"], ["2.5063", "3.14159", "1.4142", "8.1"]),
+], ids=["bounds-over-four-decades", "signs-and-integers", "restricted-symbols", "integer-mode", "never-and-once-symbols"])
+def test_gpu_batch_shared_rhs_matches_live_reference(product_lib, oracle_build, flags, targets):
+    """ries_batch with ONE enumeration of the right-hand sides for the whole batch: every report must
+    still be what the unmodified reference prints for that target alone -- equations, all three counter lines,
+    the memory line, the exit status."""
+    import ries_b200
+    from concurrent.futures import ThreadPoolExecutor
+    ref = os.path.join(oracle_build, "_ref", "ries")
+    if not os.path.exists(ref):
+        pytest.skip("no reference binary on this box")
+    got = ries_b200.batch(targets, flags + ["--no-slow-messages"], workers=4)
+    shared = ries_b200.batch_shared_stats()
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        want = list(ex.map(lambda t: run_binary(ref, flags + [t]), targets))
+    for t, (code, text), w in zip(targets, got, want):
+        shown = code & 0xff if code != 0 else 0
+        assert normalise(text) + "exit=%d\n" % shown == w, (flags, t)
+    assert shared["rhs_passes_served"] > 0, shared  # the sharing path is what ran
 
 
 def test_gpu_one_search_over_two_gpus(product_lib):
