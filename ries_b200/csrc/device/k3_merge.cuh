@@ -79,7 +79,8 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 cur = T->cur, nt = T->nt;
   const double* __restrict__ tval = D.tval[cur];
-  const Row* __restrict__ trow = D.trow[cur];
+  const u32* __restrict__ tref = D.tref[cur];
+  const Row* __restrict__ heap = D.heap;
   const u64* __restrict__ keys = D.keys[0]; /* 8 digit passes: the sorted order ends in buffer 0 */
   const u32* __restrict__ idx = D.idx[0];
   const Row* __restrict__ surv = A->gathered ? D.gdone : D.done;
@@ -89,7 +90,7 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   u32* const uniq_seq_o = D.uniq_seq;
   u32* const uniq_gap_o = D.uniq_gap;
   SeqKey* const uniq_sk_o = D.uniq_sk;
-  ASSUME_GLOBAL(tval); ASSUME_GLOBAL(trow); ASSUME_GLOBAL(keys); ASSUME_GLOBAL(idx); ASSUME_GLOBAL(surv); ASSUME_GLOBAL(surv_form);
+  ASSUME_GLOBAL(tval); ASSUME_GLOBAL(tref); ASSUME_GLOBAL(heap); ASSUME_GLOBAL(keys); ASSUME_GLOBAL(idx); ASSUME_GLOBAL(surv); ASSUME_GLOBAL(surv_form);
   ASSUME_GLOBAL(uniq_seq_o); ASSUME_GLOBAL(uniq_gap_o); ASSUME_GLOBAL(uniq_sk_o); ASSUME_GLOBAL((const u64*)state);
   const u64 epoch = (u64)(T->epoch + 8u);
   while (true) {
@@ -152,9 +153,10 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
         pos[r] = p;
         if (in_table) {
           if (!skip_exact) {
-            Row t = trow[p];
-            bool tree_is_lhs = (t.der != 0.0);
+            const u32 ref = tref[p];
+            const bool tree_is_lhs = (ref & TREF_LHS) != 0;
             if (using_x ? !tree_is_lhs : tree_is_lhs) {
+              const Row t = heap[ref & ~TREF_LHS];
               Row f = surv[s];
               if (using_x) push_event(D.events, A->cap_events, C, surv_form[s], EV_EXACT, f, t);
               else push_event(D.events, A->cap_events, C, surv_form[s], EV_EXACT, t, f);
@@ -239,15 +241,18 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
 /* K3 + merge of the new rows.  A new row's predecessor AT ITS INSERTION TIME is the old-table row below
    its gap unless a same-pass row inserted earlier already sits between them (that one is same-side, so no test
    happens: check_sides, ries.c:8496-8538).  Likewise for the successor.  "Inserted earlier" = smaller
-   insertion-order key (uniq_sk).  The row is read once: it goes to its place in the merged table, its key
-   into the side's hash set, and into the neighbour tests. */
+   insertion-order key (uniq_sk).  The row is read once: it is appended to the heap of table rows (rows never
+   move; the sorted order lives in the (value, reference) arrays), its value and reference go to their place in
+   the merged order, its key into the side's hash set, and it into the neighbour tests -- which fetch a
+   neighbour's row only when its reference says it is of the other side. */
 __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
   if (!pass_ok(C)) return;
   const u32 nu = C->n_uniq;
   const DevPtrs& D = *Dp;
   const u32 nt = T->nt;
-  const Row* __restrict__ trow = D.trow[T->cur];
-  Row* mrow = D.trow[T->cur ^ 1];
+  const u32* __restrict__ tref = D.tref[T->cur];
+  u32* mref = D.tref[T->cur ^ 1];
+  Row* heap = D.heap;
   double* mval = D.tval[T->cur ^ 1];
   const u32* __restrict__ uniq_seq = D.uniq_seq;
   const u32* __restrict__ uniq_gap = D.uniq_gap;
@@ -257,13 +262,14 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
   const double best_match0 = A->best_match0;
   u64* hs = Dp->hset[using_x ? 1 : 0];
   const u32 hlog = Dp->hset_log2[using_x ? 1 : 0];
-  ASSUME_GLOBAL(trow); ASSUME_GLOBAL(mrow); ASSUME_GLOBAL(mval); ASSUME_GLOBAL(uniq_seq); ASSUME_GLOBAL(uniq_gap);
+  ASSUME_GLOBAL(tref); ASSUME_GLOBAL(mref); ASSUME_GLOBAL(heap); ASSUME_GLOBAL(mval); ASSUME_GLOBAL(uniq_seq); ASSUME_GLOBAL(uniq_gap);
   ASSUME_GLOBAL(uniq_sk); ASSUME_GLOBAL(surv); ASSUME_GLOBAL(hs);
   for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
     const u32 g = uniq_gap[u];
     const Row f = surv[uniq_seq[u]];
-    mrow[u + g] = f;
+    heap[nt + u] = f;
     mval[u + g] = f.val;
+    mref[u + g] = (nt + u) | (using_x ? TREF_LHS : 0u);
     hset_insert(hs, hlog, key_of(f.val));
     bool test_prev = g > 0, test_next = g < nt;
     const bool nb_prev = u > 0 && uniq_gap[u - 1] == g, nb_next = u + 1 < nu && uniq_gap[u + 1] == g;
@@ -280,9 +286,10 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
     }
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !test_prev : !test_next) continue;
-      const Row o = trow[side == 0 ? g - 1 : g];
-      bool other_is_lhs = (o.der != 0.0);
+      const u32 oref = tref[side == 0 ? g - 1 : g];
+      const bool other_is_lhs = (oref & TREF_LHS) != 0;
       if (using_x ? other_is_lhs : !other_is_lhs) continue;
+      const Row o = heap[oref & ~TREF_LHS];
       const Row& L = using_x ? f : o;
       const Row& R = using_x ? o : f;
       double total = L.der - R.der;

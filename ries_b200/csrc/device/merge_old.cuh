@@ -19,7 +19,8 @@ __device__ __forceinline__ u32 warp_upper_bound_u32(const u32* __restrict__ a, u
   return lo + __popc(__ballot_sync(0xffffffffu, le));
 }
 
-/* Old rows move up by the number of new rows whose gap is at or below them.  A chunk of consecutive
+/* Old table positions -- (value, row reference) pairs, 12 bytes: the rows themselves stay where they are in the
+   heap -- move up by the number of new rows whose gap is at or below them.  A chunk of consecutive
    old rows only needs the slice of the (sorted) gap list between the counts of its first and last row:
    found by two warp searches, staged in shared memory, searched there. */
 #define MO_THREADS 256
@@ -35,11 +36,12 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
   if (nu == 0) return; /* nothing inserted: the live buffer stays as it is */
   const u32 nt = T->nt;
   const DevPtrs& D = *Dp;
-  const Row* __restrict__ trow = D.trow[T->cur];
-  Row* mrow = D.trow[T->cur ^ 1];
+  const u32* __restrict__ tref = D.tref[T->cur];
+  const double* __restrict__ tval = D.tval[T->cur];
+  u32* mref = D.tref[T->cur ^ 1];
   double* mval = D.tval[T->cur ^ 1];
   const u32* __restrict__ uniq_gap = D.uniq_gap;
-  ASSUME_GLOBAL(trow); ASSUME_GLOBAL(mrow); ASSUME_GLOBAL(mval); ASSUME_GLOBAL(uniq_gap);
+  ASSUME_GLOBAL(tref); ASSUME_GLOBAL(tval); ASSUME_GLOBAL(mref); ASSUME_GLOBAL(mval); ASSUME_GLOBAL(uniq_gap);
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   (void)lane;
   const u32 nchunks = (nt + MO_CHUNK - 1) / MO_CHUNK;
@@ -71,10 +73,9 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
             if (win[mid] <= j) a = mid + 1; else b = mid;
           }
         }
-        const Row row = trow[j];
         const u32 dst = j + lo + a;
-        mrow[dst] = row;
-        mval[dst] = row.val;
+        mval[dst] = tval[j];
+        mref[dst] = tref[j];
       }
     }
     __syncthreads();
@@ -85,11 +86,10 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
 __global__ void k_hset_rebuild(const DevPtrs* Dp, const TableState* T, int side) {
   const DevPtrs& D = *Dp;
   const u32 nt = T->nt;
-  const Row* __restrict__ trow = D.trow[T->cur];
+  const u32* __restrict__ tref = D.tref[T->cur];
+  const double* __restrict__ tval = D.tval[T->cur];
   u64* hs = Dp->hset[side];
   const u32 hlog = Dp->hset_log2[side];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
-    const Row r = trow[i];
-    if (((r.der != 0.0) ? 1 : 0) == side) hset_insert(hs, hlog, key_of(r.val));
-  }
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x)
+    if ((int)(tref[i] >> 31) == side) hset_insert(hs, hlog, key_of(tval[i]));
 }

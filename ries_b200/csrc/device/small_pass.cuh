@@ -151,7 +151,8 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
   /* classify: new distinct values, EXACT events */
   const u32 cur = T->cur, nt = T->nt;
   const double* __restrict__ tval = D.tval[cur];
-  const Row* __restrict__ trow = D.trow[cur];
+  const u32* __restrict__ tref = D.tref[cur];
+  Row* heap = D.heap;
   const int using_x = A->using_x, skip_exact = A->skip_exact;
   u32 pos[SP_ITEMS], sq[SP_ITEMS], flags = 0;
   {
@@ -195,9 +196,10 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
       const bool in_table = (p < nt) && (tval[p] == v);
       if (in_table) {
         if (!skip_exact) {
-          Row t = trow[p];
-          bool tree_is_lhs = (t.der != 0.0);
+          const u32 ref = tref[p];
+          const bool tree_is_lhs = (ref & TREF_LHS) != 0;
           if (using_x ? !tree_is_lhs : tree_is_lhs) {
+            const Row t = heap[ref & ~TREF_LHS];
             Row f = D.surv[sidx];
             if (using_x) push_event(D.events, A->cap_events, C, sidx, EV_EXACT, f, t);
             else push_event(D.events, A->cap_events, C, sidx, EV_EXACT, t, f);
@@ -241,13 +243,14 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
   __syncthreads();
   /* match (K3) and merge of the new rows */
   const double best_match0 = A->best_match0;
-  Row* mrow = D.trow[cur ^ 1];
+  u32* mref = D.tref[cur ^ 1];
   double* mval = D.tval[cur ^ 1];
   for (u32 u = tid; u < nu; u += SP_THREADS) {
     const u32 sidx = s_useq[u], g = s_ugap[u];
     const Row f = D.surv[sidx];
-    mrow[u + g] = f;
+    heap[nt + u] = f;
     mval[u + g] = f.val;
+    mref[u + g] = (nt + u) | (using_x ? TREF_LHS : 0u);
     hset_insert(Dp->hset[using_x ? 1 : 0], Dp->hset_log2[using_x ? 1 : 0], key_of(f.val)); /* later passes' pre-dedupe */
     bool test_prev = g > 0, test_next = g < nt;
     if (test_prev) {
@@ -260,9 +263,10 @@ __device__ __forceinline__ void small_post_body(const DevPtrs* Dp, const PassArg
     }
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !test_prev : !test_next) continue;
-      const Row o = trow[side == 0 ? g - 1 : g];
-      bool other_is_lhs = (o.der != 0.0);
+      const u32 oref = tref[side == 0 ? g - 1 : g];
+      const bool other_is_lhs = (oref & TREF_LHS) != 0;
       if (using_x ? other_is_lhs : !other_is_lhs) continue;
+      const Row o = heap[oref & ~TREF_LHS];
       const Row& L = using_x ? f : o;
       const Row& R = using_x ? o : f;
       double total = L.der - R.der;

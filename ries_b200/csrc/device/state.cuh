@@ -167,7 +167,8 @@ __device__ __forceinline__ bool seq_before(const SeqKey& a, const SeqKey& b) {
 #define ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
 #endif
 
-#define FORM_HOLE 0xffffu /* done_form[] / Node::form of a slot that was allocated but not filled */
+#define FORM_HOLE 0xffffu
+#define TREF_LHS 0x80000000u /* the side of a table row rides in its reference: der != 0 <=> LHS (ries.c:8496) */ /* done_form[] / Node::form of a slot that was allocated but not filled */
 
 /* Hash set of table keys, one per side: 4-slot buckets of 32 bytes (one DRAM sector per probe).  It only has to be
    SOUND: a key it reports is in the table on that side.  A key that found its bucket full is simply not
@@ -217,7 +218,8 @@ struct DevPtrs {
   SeqKey* uniq_sk; /* ... and its insertion-order key (general passes) */
   u64* hset[2];   /* per side (0 RHS, 1 LHS): hash set of the keys resident in the table, 4-slot buckets */
   u32 hset_log2[2]; /* log2 of the number of buckets */
-  Row* trow[2];
+  Row* heap;      /* the table's rows, append-only: a row never moves once inserted */
+  u32* tref[2];   /* per table position (sorted by value, ping-pong with tval): TREF_LHS | index of its row in heap[] */
   double* tval[2];
   MatchEvent* events;
   Staged* staged; /* K1 of the tiny passes: scratch, 2 x EXP_MAX_ITEMS */

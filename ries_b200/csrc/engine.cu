@@ -25,7 +25,7 @@
 //
 // Data layout in HBM (all device-resident for the whole search):
 //   nodes[]   48 B AoS, one per live prefix of the running pass (cactus stack, see params.h)
-//   table     rows 32 B AoS sorted by value + a dense 8 B key array for searches, ping-pong
+//   table     (value 8 B, row reference 4 B) sorted by value, ping-pong; the 32 B rows in an append-only heap
 //   done[]    32 B rows + 2 B form index, the pass's complete expressions in NO particular order (state.cuh, SeqKey)
 //   hset[2]   per side, a hash set of the keys resident in the table (pre-dedupe before the sort)
 // No tensor cores: nothing here is a dense contraction.
@@ -265,7 +265,8 @@ class DeviceEngine : public Engine {
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
     nodes_.release(st_); done_.release(st_); done_form_.release(st_); surv_.release(st_); uniq_sk_.release(st_);
     hset_[0].release(st_); hset_[1].release(st_); tail_.release(st_);
-    for (int b = 0; b < 2; b++) { keys_[b].release(st_); idx_[b].release(st_); trow_[b].release(st_); tval_[b].release(st_); }
+    for (int b = 0; b < 2; b++) { keys_[b].release(st_); idx_[b].release(st_); tref_[b].release(st_); tval_[b].release(st_); }
+    heap_.release(st_);
     uniq_seq_.release(st_); uniq_gap_.release(st_); events_.release(st_); staged_.release(st_);
     rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_);
     ksend_.release(st_); ksend_form_.release(st_);
@@ -1037,9 +1038,10 @@ class DeviceEngine : public Engine {
   }
   void ensure_table(size_t rows) {
     /* the live buffer keeps its contents; the other one is the merge destination */
-    if (trow_[cur_].ensure(rows, st_, true)) ptrs_dirty_ = true;
+    if (heap_.ensure(rows, st_, true)) ptrs_dirty_ = true;
+    if (tref_[cur_].ensure(rows, st_, true)) ptrs_dirty_ = true;
     if (tval_[cur_].ensure(rows, st_, true)) ptrs_dirty_ = true;
-    if (trow_[cur_ ^ 1].ensure(rows, st_)) ptrs_dirty_ = true;
+    if (tref_[cur_ ^ 1].ensure(rows, st_)) ptrs_dirty_ = true;
     if (tval_[cur_ ^ 1].ensure(rows, st_)) ptrs_dirty_ = true;
   }
   void upload_ptrs() {
@@ -1047,7 +1049,8 @@ class DeviceEngine : public Engine {
     DevPtrs& h = *h_ptrs_;
     h.P = d_P_; h.tt = d_tt_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
     h.ksend = ksend_.p; h.ksend_form = ksend_form_.p; h.shdr = d_shdr_; h.ghdr = d_ghdr_; h.tail = tail_.p;
-    for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.trow[b] = trow_[b].p; h.tval[b] = tval_[b].p; }
+    for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.tref[b] = tref_[b].p; h.tval[b] = tval_[b].p; }
+    h.heap = heap_.p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.uniq_sk = uniq_sk_.p; h.events = events_.p; h.staged = staged_.p;
     for (int sd = 0; sd < 2; sd++) { h.hset[sd] = hset_[sd].p; h.hset_log2[sd] = hset_log2_[sd]; }
     h.rs_state = rs_state_.p; h.cc_state = cc_state_.p; h.sortctl = d_sortctl_; h.opcnt = d_opcnt_;
@@ -1122,7 +1125,8 @@ class DeviceEngine : public Engine {
   DevBuf<u64> keys_[2];
   DevBuf<u32> idx_[2];
   DevBuf<u32> uniq_seq_, uniq_gap_;
-  DevBuf<Row> trow_[2];
+  DevBuf<Row> heap_;
+  DevBuf<u32> tref_[2];
   DevBuf<double> tval_[2];
   DevBuf<MatchEvent> events_;
   MatchEvent* h_head_ = 0;
