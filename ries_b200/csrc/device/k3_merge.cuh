@@ -64,10 +64,21 @@ __device__ __forceinline__ u32 warp_lower_bound(const double* __restrict__ a, u3
 #define CC_THREADS 256
 #define CC_ITEMS 8
 #define CC_CHUNK (CC_THREADS * CC_ITEMS)
-#define CC_WIN 4096
+#define CC_WIN 3072
+
+/* The first 64 bits of an insertion-order key (form, then the first eight symbol codes, first position most
+   significant): decides "who came first" between two expressions of a pass unless they share form and the first
+   eight symbols, in which case the full keys are compared. */
+__device__ __forceinline__ u64 seq_prefix(u32 form, u64 sym_lo) {
+  u64 o = (u64)form << 48;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= ((sym_lo >> (6 * i)) & 63ull) << (6 * (7 - i));
+  return o;
+}
 __global__ void __launch_bounds__(CC_THREADS)
 k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
   __shared__ double s_win[CC_WIN + 1];
+  __shared__ u64 s_ord[CC_CHUNK]; /* seq_prefix of the chunk's keys that have an equal neighbour */
   __shared__ u32 s_cnt[CC_ITEMS * (CC_THREADS / 32)];
   __shared__ u32 s_chunk, s_base, s_lo, s_hi;
   stage_stamp(C, 2);
@@ -118,6 +129,19 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
     const u32 S = (wload + CC_WIN - 1) / CC_WIN > 1 ? (wload + CC_WIN - 1) / CC_WIN : 1;
     const u32 ns = (wload + S - 1) / S;
     for (u32 j = tid; j < ns; j += CC_THREADS) s_win[j] = tval[lo + j * S];
+    /* every key with an equal neighbour fetches the head of its own insertion-order key -- all at once, instead of
+       the first key of a run fetching them one after the other while it walks the run */
+#pragma unroll
+    for (int r = 0; r < CC_ITEMS; r++) {
+      const u32 i = base + r * CC_THREADS + tid;
+      if (i < n) {
+        const u64 k = keys[i];
+        if ((i > 0 && keys[i - 1] == k) || (i + 1 < n && keys[i + 1] == k)) {
+          const u32 s = idx[i];
+          s_ord[r * CC_THREADS + tid] = seq_prefix(surv_form[s], surv[s].sym.lo);
+        }
+      }
+    }
     __syncthreads();
     u32 pos[CC_ITEMS], sq[CC_ITEMS];
     u32 flags = 0;
@@ -167,13 +191,14 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
           /* the run of this value: the expression inserted first wins */
           if (i + 1 < n && keys[i + 1] == k) {
             u32 w = s;
-            Sym128 ws = surv[w].sym;
-            u32 wf = surv_form[w];
+            u64 wo = s_ord[i - base];
+            const u32 cend = base + CC_CHUNK;
             for (u32 j = i + 1; j < n && keys[j] == k; j++) {
               const u32 s2 = idx[j];
-              const Sym128 s2s = surv[s2].sym;
-              const u32 s2f = surv_form[s2];
-              if (seq_before(s2f, s2s, wf, ws)) { w = s2; ws = s2s; wf = s2f; }
+              const u64 o2 = (j < cend) ? s_ord[j - base] : seq_prefix(surv_form[s2], surv[s2].sym.lo);
+              bool before = o2 < wo;
+              if (o2 == wo) before = seq_before(surv_form[s2], surv[s2].sym, surv_form[w], surv[w].sym);
+              if (before) { w = s2; wo = o2; }
             }
             sq[r] = w;
           }
