@@ -237,11 +237,15 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
         /* from the END of the list: the queues are in slot order and the heavy operators of a class (^ v L A, the
            trigonometric functions) are its last slots, so they start first and the constants fill the tail */
         b = nb_total - 1u - b;
-        /* queue of batch b: the last q with s_cum[q] <= b (s_cum is non-decreasing, s_cum[nq] = nb_total) */
+        /* queue of batch b: the last q with s_cum[q] <= b (s_cum is non-decreasing, s_cum[0] = 0): the lanes look at
+           three queues each and count */
         u32 q = 0;
 #pragma unroll
-        for (int s = 64; s > 0; s >>= 1)
-          if (q + s < nq && s_cum[q + s] <= b) q += s;
+        for (int j = 0; j < 3; j++) {
+          const u32 qq = (u32)j * 32 + lane;
+          q += __popc(__ballot_sync(0xffffffffu, qq < nq && s_cum[qq] <= b));
+        }
+        q -= 1u;
         const u32 j0 = (b - s_cum[q]) * 32u + lane;      /* index in the queue, from its head */
         const u32 avail = s_tail[q] - head[q];
         const bool act = j0 < avail;
