@@ -77,7 +77,8 @@ __device__ __forceinline__ u64 seq_prefix(u32 form, u64 sym_lo) {
 }
 __global__ void __launch_bounds__(CC_THREADS)
 k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
-  __shared__ double s_win[CC_WIN + 1];
+  __shared__ __align__(16) double s_winraw[CC_WIN + 4];
+  __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ u64 s_ord[CC_CHUNK]; /* seq_prefix of the chunk's keys that have an equal neighbour */
   __shared__ u32 s_cnt[CC_ITEMS * (CC_THREADS / 32)];
   __shared__ u32 s_chunk, s_base, s_lo, s_hi;
@@ -98,6 +99,9 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
   const uint16_t* __restrict__ surv_form = A->gathered ? D.gdone_form : D.done_form;
   const int using_x = A->using_x, skip_exact = A->skip_exact;
   volatile u64* state = (volatile u64*)D.cc_state;
+  if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+  u32 mbar_phase = 0;
+  __syncthreads();
   u32* const uniq_seq_o = D.uniq_seq;
   u32* const uniq_gap_o = D.uniq_gap;
   SeqKey* const uniq_sk_o = D.uniq_sk;
@@ -128,7 +132,15 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
        search runs over the samples there and finishes among the S keys between two samples in global memory */
     const u32 S = (wload + CC_WIN - 1) / CC_WIN > 1 ? (wload + CC_WIN - 1) / CC_WIN : 1;
     const u32 ns = (wload + S - 1) / S;
-    for (u32 j = tid; j < ns; j += CC_THREADS) s_win[j] = tval[lo + j * S];
+    /* a contiguous window is fetched by ONE bulk asynchronous copy (16-byte granules: from the even index at or
+       below lo), which runs under the fetch of the order keys below; a sampled window is gathered by the threads */
+    const u32 lo_al = lo & ~1u;
+    const double* s_win = s_winraw + (S == 1 ? lo - lo_al : 0u);
+    if (S == 1) {
+      if (tid == 0) bulk_g2s(s_winraw, tval + lo_al, (((wload + (lo - lo_al)) + 1u) & ~1u) * (u32)sizeof(double), &s_mbar);
+    } else {
+      for (u32 j = tid; j < ns; j += CC_THREADS) s_winraw[j] = tval[lo + j * S];
+    }
     /* every key with an equal neighbour fetches the head of its own insertion-order key -- all at once, instead of
        the first key of a run fetching them one after the other while it walks the run */
 #pragma unroll
@@ -142,6 +154,7 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
         }
       }
     }
+    if (S == 1) { mbar_wait(&s_mbar, mbar_phase); mbar_phase ^= 1u; }
     __syncthreads();
     u32 pos[CC_ITEMS], sq[CC_ITEMS];
     u32 flags = 0;

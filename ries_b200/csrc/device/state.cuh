@@ -167,6 +167,26 @@ __device__ __forceinline__ bool seq_before(const SeqKey& a, const SeqKey& b) {
 #define ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
 #endif
 
+/* Bulk asynchronous copy global -> shared (the TMA engine's 1-D path, SASS UBLKCP) completing on an mbarrier: one
+   thread issues it, nobody's registers or issue slots are spent on the transfer, and the block does something
+   else until it needs the data.  Source, destination and size must be multiples of 16 bytes. */
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 #define FORM_HOLE 0xffffu
 #define TREF_LHS 0x80000000u /* the side of a table row rides in its reference: der != 0 <=> LHS (ries.c:8496) */ /* done_form[] / Node::form of a slot that was allocated but not filled */
 
