@@ -29,7 +29,8 @@ __device__ __forceinline__ u32 warp_upper_bound_u32(const u32* __restrict__ a, u
 #define MO_WIN 4096
 __global__ void __launch_bounds__(MO_THREADS)
 k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
-  __shared__ u32 s_win[MO_WIN];
+  __shared__ __align__(16) u32 s_winraw[MO_WIN + 8];
+  __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ u32 s_lo, s_hi;
   if (C->overflow) return;
   const u32 nu = C->n_uniq;
@@ -45,6 +46,9 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   (void)lane;
   const u32 nchunks = (nt + MO_CHUNK - 1) / MO_CHUNK;
+  if (tid == 0) mbar_init(&s_mbar, 1);
+  u32 mbar_phase = 0;
+  __syncthreads();
   for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const u32 base = chunk * MO_CHUNK;
     const u32 last = min(base + MO_CHUNK, nt) - 1;
@@ -58,10 +62,20 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
     __syncthreads();
     const u32 lo = s_lo, wn = s_hi - s_lo;
     const bool in_smem = wn <= MO_WIN;
-    if (in_smem)
-      for (u32 j = tid; j < wn; j += MO_THREADS) s_win[j] = uniq_gap[lo + j];
-    __syncthreads();
-    const u32* win = in_smem ? s_win : uniq_gap + lo;
+    /* the slice of the gap list arrives by one bulk asynchronous copy (16-byte granules: from the multiple of four
+       at or below lo) while the threads fetch the chunk's (value, reference) pairs */
+    const u32 lo_al = lo & ~3u;
+    if (in_smem && wn && tid == 0) bulk_g2s(s_winraw, uniq_gap + lo_al, (((wn + (lo - lo_al)) + 3u) & ~3u) * 4u, &s_mbar);
+    double tv[MO_ITEMS];
+    u32 tr[MO_ITEMS];
+#pragma unroll
+    for (int r = 0; r < MO_ITEMS; r++) {
+      const u32 j = base + r * MO_THREADS + tid;
+      tv[r] = (j < nt) ? tval[j] : 0.0;
+      tr[r] = (j < nt) ? tref[j] : 0u;
+    }
+    if (in_smem && wn) { mbar_wait(&s_mbar, mbar_phase); mbar_phase ^= 1u; }
+    const u32* win = in_smem ? s_winraw + (lo - lo_al) : uniq_gap + lo;
 #pragma unroll
     for (int r = 0; r < MO_ITEMS; r++) {
       const u32 j = base + r * MO_THREADS + tid;
@@ -74,8 +88,8 @@ k_merge_old(const DevPtrs* Dp, const PassCtl* C, const TableState* T) {
           }
         }
         const u32 dst = j + lo + a;
-        mval[dst] = tval[j];
-        mref[dst] = tref[j];
+        mval[dst] = tv[r];
+        mref[dst] = tr[r];
       }
     }
     __syncthreads();

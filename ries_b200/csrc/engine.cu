@@ -1029,7 +1029,7 @@ class DeviceEngine : public Engine {
     ch |= done_form_.ensure(done_.cap, st_);
     for (int b = 0; b < 2; b++) { ch |= keys_[b].ensure(done_.cap, st_); ch |= idx_[b].ensure(done_.cap, st_); }
     ch |= uniq_seq_.ensure(done_.cap, st_);
-    ch |= uniq_gap_.ensure(done_.cap, st_);
+    ch |= uniq_gap_.ensure(done_.cap + 16, st_); /* + slack: bulk copies read whole 16-byte granules */
     ch |= uniq_sk_.ensure(done_.cap, st_);
     /* look-back state must start as zeros (stale bits must not look like a live epoch / status) */
     ch |= rs_state_.ensure((done_.cap / RS_CHUNK + 2) * 256, st_, false, true);
@@ -1039,10 +1039,10 @@ class DeviceEngine : public Engine {
   void ensure_table(size_t rows) {
     /* the live buffer keeps its contents; the other one is the merge destination */
     if (heap_.ensure(rows, st_, true)) ptrs_dirty_ = true;
-    if (tref_[cur_].ensure(rows, st_, true)) ptrs_dirty_ = true;
-    if (tval_[cur_].ensure(rows, st_, true)) ptrs_dirty_ = true;
-    if (tref_[cur_ ^ 1].ensure(rows, st_)) ptrs_dirty_ = true;
-    if (tval_[cur_ ^ 1].ensure(rows, st_)) ptrs_dirty_ = true;
+    if (tref_[cur_].ensure(rows + 16, st_, true)) ptrs_dirty_ = true; /* + slack: bulk copies read whole 16-byte granules */
+    if (tval_[cur_].ensure(rows + 16, st_, true)) ptrs_dirty_ = true;
+    if (tref_[cur_ ^ 1].ensure(rows + 16, st_)) ptrs_dirty_ = true;
+    if (tval_[cur_ ^ 1].ensure(rows + 16, st_)) ptrs_dirty_ = true;
   }
   void upload_ptrs() {
     CUDA_CHECK(cudaStreamSynchronize(st_)); /* h_ptrs_ may still be in flight from the last upload */
