@@ -275,9 +275,14 @@ def batch_object(args, ries_b200, rank, world, dist, torch):
     if dist is not None:
         torch.cuda.synchronize()
         dist.barrier()
-    t0 = time.perf_counter()
-    got = ries_b200.batch(mine, flags, workers=args.workers)
-    wall = time.perf_counter() - t0
+    walls = []
+    for _ in range(3):  # the median of three batches (run-to-run spread is large: 16 host threads share the driver)
+        t0 = time.perf_counter()
+        got = ries_b200.batch(mine, flags, workers=args.workers)
+        walls.append(time.perf_counter() - t0)
+        if dist is not None:
+            dist.barrier()
+    wall = sorted(walls)[1]
     exprs = sum(parse_expressions(text) for _, text in got)
     checked, same = 0, 0
     gpath = os.path.join(ROOT, "tests", "golden", "batch_l%s.json" % level)
@@ -302,6 +307,7 @@ def batch_object(args, ries_b200, rank, world, dist, torch):
             "targets": int(nt), "seconds": wall, "targets_per_sec": nt / wall, "targets_per_sec_per_gpu": nt / wall / world,
             "expr_per_sec": exprs / wall, "reports_checked_against_reference": int(checked),
             "reports_identical": int(same), "shared_rhs": ries_b200.batch_shared_stats(),
+            "seconds_is": "median of three batches", "seconds_each_rank0": [round(w, 4) for w in walls],
             "api": "ries_batch(targets, flags, workers, done_cb) via ctypes"}
 
 

@@ -807,7 +807,7 @@ class DeviceEngine : public Engine {
       const u32 want = pass_seq_;
       for (unsigned spins = 1;; spins++) {
         if (*seq == want) break;
-        if ((spins & 0xfffu) == 0) {
+        if ((spins & 0x3ffffu) == 0) { /* every few milliseconds: a driver call takes the lock the launching threads of a batch need */
           const cudaError_t q = cudaStreamQuery(st_);
           if (q == cudaSuccess) {
             if (*seq == want) break;
