@@ -40,6 +40,8 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
   const bool gathered = A->gathered != 0;
   const u32 bound = gathered ? (u32)A->shard_bound : 1u;
   const SlotHdr* __restrict__ ghdr = D.ghdr;
+  const bool ranged = gathered && A->range_split != 0;
+  const u64 klo = C->klo, khi = C->khi;
   u64* keys = D.keys[0];
   u32* idx = D.idx[0];
   ASSUME_GLOBAL(done); ASSUME_GLOBAL(done_form); ASSUME_GLOBAL(hs); ASSUME_GLOBAL(keys); ASSUME_GLOBAL(idx); ASSUME_GLOBAL(ghdr);
@@ -57,7 +59,7 @@ k_keys(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
         const bool filled = gathered ? (i % bound) < ghdr[i / bound].n_kept : done_form[i] != FORM_HOLE;
         if (filled) {
           k[r] = key_of(done[i].val);
-          keep = !hset_contains(hs, hlog, k[r]);
+          keep = (!ranged || (k[r] >= klo && k[r] < khi)) && !hset_contains(hs, hlog, k[r]);
         }
       }
       const u32 b = __ballot_sync(0xffffffffu, keep);

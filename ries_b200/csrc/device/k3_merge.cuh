@@ -283,7 +283,9 @@ k_classify_compact(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const Table
    move; the sorted order lives in the (value, reference) arrays), its value and reference go to their place in
    the merged order, its key into the side's hash set, and it into the neighbour tests -- which fetch a
    neighbour's row only when its reference says it is of the other side. */
-__global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T) {
+/* mode 0: both halves (every pass but the range-split ones); mode 1: the neighbour tests only, on this rank's
+   value range; mode 2: the merge only, on the new rows of all ranges after the second exchange (shard.cuh) */
+__global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl* C, const TableState* T, int mode) {
   if (!pass_ok(C)) return;
   const u32 nu = C->n_uniq;
   const DevPtrs& D = *Dp;
@@ -305,10 +307,13 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
   for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
     const u32 g = uniq_gap[u];
     const Row f = surv[uniq_seq[u]];
-    heap[nt + u] = f;
-    mval[u + g] = f.val;
-    mref[u + g] = (nt + u) | (using_x ? TREF_LHS : 0u);
-    hset_insert(hs, hlog, key_of(f.val));
+    if (mode != 1) {
+      heap[nt + u] = f;
+      mval[u + g] = f.val;
+      mref[u + g] = (nt + u) | (using_x ? TREF_LHS : 0u);
+      hset_insert(hs, hlog, key_of(f.val));
+    }
+    if (mode == 2) continue;
     bool test_prev = g > 0, test_next = g < nt;
     const bool nb_prev = u > 0 && uniq_gap[u - 1] == g, nb_next = u + 1 < nu && uniq_gap[u + 1] == g;
     if ((test_prev && nb_prev) || (test_next && nb_next)) {

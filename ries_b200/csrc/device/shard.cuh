@@ -112,8 +112,85 @@ __global__ void k_gather_hdr(const DevPtrs* D, const PassArgs* A, PassCtl* C, Ta
     C->dead = dead; C->gen = gen;
     C->max_nodes = max_nodes; C->max_done = max_done; C->n_kept = max_kept;
     C->n_keys = 0; C->chunk_ticket = 0; C->aux_ticket = 0; C->tile_ticket = 0; C->blocks_done = 0;
+    C->n_events = 0; C->n_uniq = 0;
+    C->klo = 0; C->khi = ~0ull;
+    if (A->range_split) {
+      /* this rank's value range: between the table's values at its quantiles, so that every gap of the table --
+         and with it every neighbour test and every run of equal values -- belongs to exactly one rank */
+      const u32 nt = T->nt;
+      const double* tv = D->tval[T->cur];
+      const u32 r = (u32)A->shard_rank, w = (u32)world;
+      if (r > 0) C->klo = key_of(tv[(u64)nt * r / w]);
+      if (r + 1 < w) C->khi = key_of(tv[(u64)nt * (r + 1) / w]);
+    }
     u32 e = (T->epoch + 16) & 0x3ffffff0u;
     if (e == 0) e = 16;
     T->epoch = e;
+  }
+}
+
+/* ---- second half of a sharded pass, split by value range -------------------------------------------------- */
+/* The table stays replicated (its per-pass merge moves 12 bytes per row), but sorting, deduping and matching the
+   gathered rows is split: rank r takes the rows whose value lies between the table's values at its quantiles
+   (k_keys' range filter), sorts and classifies them, runs the neighbour tests of its new rows (k_match_merge_new,
+   mode 1) -- and then the ranks exchange what they found, which is small: (index into the gathered rows, gap) per new
+   row, and the candidates.  k_gather2 strings the ranges together (they are in value order by rank), and the merge
+   (mode 2, k_merge_old), the refinement and the end of the pass run replicated on identical data as before. */
+__global__ void k_send2_hdr(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
+  if (threadIdx.x != 0) return;
+  SlotHdr h;
+  h.overflow = C->overflow;
+  h.n_kept = C->n_uniq;
+  h.node_count = C->n_events;
+  if (C->n_uniq > (u32)A->range_bound) h.overflow |= OVF_KEPT;
+  if (C->n_events > (u32)A->range_ebound) h.overflow |= OVF_EVENTS;
+  h.done_slots = 0; h.dead = 0; h.gen = 0;
+  for (int i = 0; i < 8; i++) h.pad[i] = 0;
+  *Dp->shdr = h;
+}
+
+__global__ void __launch_bounds__(256)
+k_gather2(const DevPtrs* Dp, const PassArgs* A, PassCtl* C) {
+  __shared__ u32 s_off[RIES_MAX_RANKS + 1], s_eoff[RIES_MAX_RANKS + 1];
+  const DevPtrs& D = *Dp;
+  const int world = A->shard_world;
+  const SlotHdr* g = D.ghdr2;
+  if (threadIdx.x == 0) {
+    u32 off = 0, eoff = 0;
+    for (int r = 0; r < world; r++) { s_off[r] = off; s_eoff[r] = eoff; off += g[r].n_kept; eoff += g[r].node_count; }
+    s_off[world] = off; s_eoff[world] = eoff;
+  }
+  __syncthreads();
+  u32 ovf = 0;
+  for (int r = 0; r < world; r++) ovf |= g[r].overflow;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    C->overflow |= ovf;
+    C->n_uniq = s_off[world];
+    C->n_events = s_eoff[world];
+    if (s_eoff[world] > A->cap_events) C->overflow |= OVF_EVENTS;
+    u32 mk = 0, me = 0;
+    for (int r = 0; r < world; r++) { mk = max(mk, g[r].n_kept); me = max(me, g[r].node_count); }
+    C->max_new = mk;
+    C->max_ev = me;
+  }
+  if (ovf) return;
+  const u32 bound = (u32)A->range_bound, eb = (u32)A->range_ebound;
+  const Row* __restrict__ gd = D.gdone;
+  const uint16_t* __restrict__ gf = D.gdone_form;
+  for (int r = 0; r < world; r++) {
+    const u32 n = g[r].n_kept, o = s_off[r];
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+      const u32 gi = D.g2_idx[(size_t)r * bound + j];
+      D.uniq_seq[o + j] = gi;
+      D.uniq_gap[o + j] = D.g2_gap[(size_t)r * bound + j];
+      SeqKey sk;
+      const Sym128 sy = gd[gi].sym;
+      sk.lo = sy.lo; sk.hi = sy.hi; sk.form = gf[gi]; sk.pad = 0;
+      D.uniq_sk[o + j] = sk;
+    }
+    const u32 ne = g[r].node_count, eo = s_eoff[r];
+    if (s_eoff[world] <= A->cap_events)
+      for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < ne; j += gridDim.x * blockDim.x)
+        D.events[eo + j] = D.g2_events[(size_t)r * eb + j];
   }
 }

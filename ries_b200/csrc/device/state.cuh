@@ -56,6 +56,9 @@ struct PassArgs {
      the regroup kernels read the all-gathered complete expressions instead of this rank's own */
   int shard_rank, shard_world, gathered;
   int shard_bound; /* rows per rank in the exchange of a sharded pass (send slot, stride of the gathered array) */
+  /* sharded pass, second half split by VALUE RANGE (shard.cuh): this rank sorts, dedupes and matches only the
+     gathered rows whose value lies in its range; rows per rank / candidates per rank in the second exchange */
+  int range_split, range_bound, range_ebound, pad_rs;
   /* RHS pass enumerated once for a whole batch of targets (engine.cu, SharedRhs): `der` of an RHS prefix carries
      M = max |value| along the prefix, and what depends on a target's overflow bound is recorded (TailRec) for
      every prefix / child with M >= p_min, the smallest bound in the batch */
@@ -82,6 +85,8 @@ struct PassCtl {
   u32 max_nodes, max_done; /* sharded passes: the largest rank's node and expression slots (arena sizing) */
   u32 n_tail;              /* TailRec records written (may exceed the capacity: then OVF_TAIL is set) */
   u32 bar_gen;             /* k_expand_all: grid-barrier generation (monotonic, survives passes) */
+  u64 klo, khi;            /* sharded pass split by value range: this rank keeps the keys in [klo, khi) */
+  u32 max_new, max_ev;     /* ... the largest range's new rows and candidates (slot sizes of the next pass) */
   /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] regroup +
      sort, [2] classify/match/merge, [3] refine, [4] end.  Written by thread 0 of block 0 of the stage's first
      kernel (the kernels of a pass run back to back on one stream), read by the host from the copied-back
@@ -230,6 +235,10 @@ struct DevPtrs {
   uint16_t* ksend_form;
   SlotHdr* shdr;
   SlotHdr* ghdr;
+  SlotHdr* ghdr2;        /* second exchange of a range-split pass: headers, new rows (index, gap), candidates */
+  u32* g2_idx;
+  u32* g2_gap;
+  MatchEvent* g2_events;
   TailRec* tail;  /* shared RHS passes being built: bound-dependent records */ /* ... and the gathered headers, one per rank */
   u64* keys[2];
   u32* idx[2];

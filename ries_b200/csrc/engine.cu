@@ -244,6 +244,10 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMallocHost(&h_args2_, sizeof(PassArgs)));
     CUDA_CHECK(cudaMalloc(&d_shdr_, sizeof(SlotHdr)));
     CUDA_CHECK(cudaMalloc(&d_ghdr_, RIES_MAX_RANKS * sizeof(SlotHdr)));
+    CUDA_CHECK(cudaMalloc(&d_ghdr2_, RIES_MAX_RANKS * sizeof(SlotHdr)));
+    CUDA_CHECK(cudaMemset(d_ghdr2_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
+    use_range_ = getenv("RIES_NO_RANGE_SPLIT") == 0; /* A/B, test hook: the whole second half replicated */
+    if (const char* e = getenv("RIES_RANGE_MIN")) range_min_ = std::max(16u, (u32)strtoul(e, 0, 10)); /* test hook */
     CUDA_CHECK(cudaMemset(d_ghdr_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
     if (const char* e = getenv("RIES_SHARD_MIN")) shard_min_ = (u32)atol(e);
     memset(h_ptrs_, 0, sizeof(DevPtrs));
@@ -271,7 +275,8 @@ class DeviceEngine : public Engine {
     rs_state_.release(st_); cc_state_.release(st_); gdone_.release(st_); gdone_form_.release(st_);
     ksend_.release(st_); ksend_form_.release(st_);
     cudaStreamSynchronize(st_);
-    cudaFreeHost(h_args2_); cudaFree(d_shdr_); cudaFree(d_ghdr_);
+    cudaFreeHost(h_args2_); cudaFree(d_shdr_); cudaFree(d_ghdr_); cudaFree(d_ghdr2_);
+    g2_idx_.release(st_); g2_gap_.release(st_); g2_events_.release(st_);
     cudaFree(d_P_); cudaFree(d_tt_); cudaFree(d_out_); cudaFree(d_passin_); cudaFree(d_tab_); cudaFree(d_ptrs_); cudaFree(d_sortctl_);
     cudaFree(d_opcnt_);
     cudaFreeHost(h_out_); cudaFreeHost(h_passin_); cudaFreeHost(h_ptrs_);
@@ -333,6 +338,7 @@ class DeviceEngine : public Engine {
     }
     prev_nodes_[0] = prev_nodes_[1] = prev_done_[0] = prev_done_[1] = 0;
     prev_gen_[0] = prev_gen_[1] = prev_keys_[0] = prev_keys_[1] = shard_kept_[0] = shard_kept_[1] = 0;
+    range_new_[0] = range_new_[1] = 0;
     kernel_launches = 0;
     h2d_bytes = sizeof(P);
     d2h_bytes = 0;
@@ -400,7 +406,7 @@ class DeviceEngine : public Engine {
     const int side = using_x ? 1 : 0;
     bool no_tiny = !use_small_post_;
     unsigned long long gen_k1 = 0; /* sharded passes: complete expressions of all ranks' K1, before the pre-dedupe */
-    bool was_sharded = false, was_tiny = false, was_shared = false;
+    bool was_sharded = false, was_tiny = false, was_shared = false, was_ranged = false;
     {
       /* sizes grow ~1.3-1.6x per complexity step: keep twice the previous same-side pass in hand, so that
          the overflow-and-rerun path stays the exception (it costs a whole pass) */
@@ -437,6 +443,11 @@ class DeviceEngine : public Engine {
       const u32 bound = shard ? shard_bound(side, shard_world) : 0;
       h_args_->shard_bound = (int)bound;
       h_args_->track_m = 0; h_args_->cap_tail = 0; h_args_->p_min = 0;
+      /* a sharded pass's second half is split by value range once the table has quantiles worth the name */
+      const bool range = shard && use_range_ && nt_ >= range_min_;
+      const u32 rbound = range ? range_bound(side, shard_world) : 0, rebound = range ? range_ebound_ : 0;
+      h_args_->range_split = range ? 1 : 0;
+      h_args_->range_bound = (int)rbound; h_args_->range_ebound = (int)rebound; h_args_->pad_rs = 0;
       /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh); force_small_post_ is the
          test hook that mispredicts, to exercise the rerun through the general kernels */
       const bool tiny = !shard && !no_tiny && !stage_events_ &&
@@ -494,7 +505,9 @@ class DeviceEngine : public Engine {
            back half -- all enqueued at once, no host round trip in between (shard.cuh) */
         if (host_prof_) hp_t1 = now_us();
         sharded_front(max_len, small, bound, shard_world);
-        launch_stages(1, 3, max_len, small, false);
+        if (range) range_back(max_len, small, rbound, rebound, shard_world);
+        else { gather_hdr(); launch_stages(1, 3, max_len, small, false); }
+        was_ranged = range;
         if (host_prof_) hp_t2 = now_us();
         wait_pass();
         if (host_prof_) hp_t3 = now_us();
@@ -520,7 +533,11 @@ class DeviceEngine : public Engine {
       if (ovf & OVF_NODES) want_nodes = std::max<size_t>(nodes_.cap * 2, (size_t)(was_sharded ? h_ctl_->max_nodes : h_ctl_->node_count) * 2);
       if (ovf & OVF_DONE) want_done = std::max<size_t>(done_.cap * 2, (size_t)(was_sharded ? h_ctl_->max_done : h_ctl_->done_count) * 2);
       if (ovf & (OVF_NODES | OVF_DONE)) grow_arena(want_nodes, want_done);
-      if (ovf & OVF_KEPT) shard_kept_[side] = std::max<u32>(h_ctl_->n_kept, shard_kept_[side] * 2);
+      if (ovf & OVF_KEPT) {
+        shard_kept_[side] = std::max<u32>(h_ctl_->n_kept, shard_kept_[side] * 2);
+        if (was_ranged) range_new_[side] = std::max<u32>(h_ctl_->max_new, range_new_[side] * 2 + 1024);
+      }
+      if ((ovf & OVF_EVENTS) && was_ranged) range_ebound_ = std::max<u32>(range_ebound_ * 2, h_ctl_->max_ev + 64);
       if (ovf & OVF_EVENTS) {
         if (events_.ensure((size_t)h_ctl_->n_events + 1024, st_)) ptrs_dirty_ = true;
         /* the merge kernels had already entered this pass's new keys into the hash set, but the table was not
@@ -549,6 +566,7 @@ class DeviceEngine : public Engine {
     prev_gen_[side] = (u32)std::min<unsigned long long>(gen, 0xffffffffull);
     prev_keys_[side] = h_ctl_->n_keys;
     shard_kept_[side] = was_sharded ? h_ctl_->n_kept : 0;
+    range_new_[side] = was_ranged ? h_ctl_->max_new : 0;
     prev_new_[side] = nu;
     side_rows_[side] += nu;
     expand_nodes += h_ctl_->node_count;
@@ -689,7 +707,7 @@ class DeviceEngine : public Engine {
         break;
       case 2:
         k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
-        k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+        k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, 0);
         k_merge_old<<<small == 1 ? 48u : std::max(48u, wide_grid_ / div), MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
         break;
       case 3:
@@ -985,10 +1003,70 @@ class DeviceEngine : public Engine {
     memcpy(h_args2_, h_args_, sizeof(PassArgs));
     h_args2_->gathered = 1;
     CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_args2_, sizeof(PassArgs), cudaMemcpyHostToDevice, st_));
+  }
+
+  void gather_hdr() {
     bump_epoch();
     k_gather_hdr<<<1, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
     kernel_launches += 1;
     stage_launches[1] += 1;
+  }
+
+  /* rows per rank in the second exchange of a range-split pass: from the largest range's new rows in the side's last
+     such pass, else from the side's last pass as a whole */
+  u32 range_bound(int side, int world) {
+    size_t est = range_new_[side] ? (size_t)range_new_[side] * 3 / 2 : ((size_t)prev_new_[side] * 2 / (size_t)world) * 3 / 2;
+    est = std::max<size_t>(est, 4096);
+    return (u32)((est + 1023) & ~(size_t)1023);
+  }
+
+  /* Second half of a sharded pass split by value range (shard.cuh): keys + sort + classify + neighbour tests on
+     this rank's range of the gathered rows, the second (small) exchange, then the replicated merge, refinement and
+     end of the pass.  Enqueued at once like the rest. */
+  void range_back(int max_len, int small, u32 rbound, u32 ebound, int world) {
+    const DistState& ds = dist_state();
+    const bool fake = ds.fake_world > 1;
+    bool ch = false;
+    ch |= g2_idx_.ensure((size_t)world * rbound, st_);
+    ch |= g2_gap_.ensure((size_t)world * rbound, st_);
+    ch |= g2_events_.ensure((size_t)world * ebound, st_);
+    if (events_.cap < ebound) ch |= events_.ensure(ebound, st_);
+    if (ch || ptrs_dirty_) { ptrs_dirty_ = true; upload_ptrs(); }
+    const u32 g_wide = small ? 12u : wide_grid_;
+    auto local_back = [&]() {
+      gather_hdr();
+      launch_stages(1, 1, max_len, small, false);
+      k_classify_compact<<<g_wide, CC_THREADS, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_);
+      k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, 1);
+      k_send2_hdr<<<1, 32, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
+      kernel_launches += 3;
+      stage_launches[2] += 3;
+    };
+    if (fake) {
+      for (int r = 0; r < world; r++) {
+        CUDA_CHECK(cudaStreamSynchronize(st_)); /* the pinned arguments are about to change */
+        h_args2_->shard_rank = r;
+        CUDA_CHECK(cudaMemcpyAsync(d_passin_, h_args2_, sizeof(PassArgs), cudaMemcpyHostToDevice, st_));
+        local_back();
+        CUDA_CHECK(cudaMemcpyAsync(g2_idx_.p + (size_t)r * rbound, uniq_seq_.p, (size_t)rbound * sizeof(u32), cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(g2_gap_.p + (size_t)r * rbound, uniq_gap_.p, (size_t)rbound * sizeof(u32), cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(g2_events_.p + (size_t)r * ebound, events_.p, (size_t)ebound * sizeof(MatchEvent), cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(d_ghdr2_ + r, d_shdr_, sizeof(SlotHdr), cudaMemcpyDeviceToDevice, st_));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+    } else {
+      local_back();
+      dist_allgather4(d_shdr_, d_ghdr2_, sizeof(SlotHdr), uniq_seq_.p, g2_idx_.p, (size_t)rbound * sizeof(u32),
+                      uniq_gap_.p, g2_gap_.p, (size_t)rbound * sizeof(u32), events_.p, g2_events_.p,
+                      (size_t)ebound * sizeof(MatchEvent), st_);
+      gather_bytes += (unsigned long long)world * ((size_t)rbound * 8 + (size_t)ebound * sizeof(MatchEvent));
+    }
+    k_gather2<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_);
+    k_match_merge_new<<<g_wide, 256, 0, st_>>>(d_ptrs_, d_args_, d_ctl_, d_tab_, 2);
+    k_merge_old<<<small ? 48u : wide_grid_, MO_THREADS, 0, st_>>>(d_ptrs_, d_ctl_, d_tab_);
+    kernel_launches += 3;
+    stage_launches[2] += 3;
+    launch_stages(3, 3, max_len, small, false);
   }
 
   /* The hash sets restart small with every search and grow with the side's row count: at most half full after
@@ -1049,6 +1127,7 @@ class DeviceEngine : public Engine {
     DevPtrs& h = *h_ptrs_;
     h.P = d_P_; h.tt = d_tt_; h.forms = d_forms_; h.nodes = nodes_.p; h.done = done_.p; h.done_form = done_form_.p; h.gdone = gdone_.p; h.gdone_form = gdone_form_.p; h.surv = surv_.p;
     h.ksend = ksend_.p; h.ksend_form = ksend_form_.p; h.shdr = d_shdr_; h.ghdr = d_ghdr_; h.tail = tail_.p;
+    h.ghdr2 = d_ghdr2_; h.g2_idx = g2_idx_.p; h.g2_gap = g2_gap_.p; h.g2_events = g2_events_.p;
     for (int b = 0; b < 2; b++) { h.keys[b] = keys_[b].p; h.idx[b] = idx_[b].p; h.tref[b] = tref_[b].p; h.tval[b] = tval_[b].p; }
     h.heap = heap_.p;
     h.uniq_seq = uniq_seq_.p; h.uniq_gap = uniq_gap_.p; h.uniq_sk = uniq_sk_.p; h.events = events_.p; h.staged = staged_.p;
@@ -1118,6 +1197,12 @@ class DeviceEngine : public Engine {
   PassArgs* h_args2_ = 0; /* pinned: the scalars of a sharded pass's replicated half */
   SlotHdr* d_shdr_ = 0;   /* this rank's send-slot header; the gathered headers (RIES_MAX_RANKS) */
   SlotHdr* d_ghdr_ = 0;
+  SlotHdr* d_ghdr2_ = 0;  /* second exchange of a range-split pass */
+  DevBuf<u32> g2_idx_, g2_gap_;
+  DevBuf<MatchEvent> g2_events_;
+  bool use_range_ = true;
+  u32 range_min_ = 65536; /* table rows from which the second half of a sharded pass is split by value range */
+  u32 range_new_[2] = {0, 0}, range_ebound_ = 256;
   u32 prev_gen_[2] = {0, 0}, prev_keys_[2] = {0, 0}, shard_kept_[2] = {0, 0};
   u32 shard_min_ = 100000; /* complete expressions in the previous same-side pass from which a pass is sharded */
   DevBuf<u64> rs_state_, cc_state_;

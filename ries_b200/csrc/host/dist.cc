@@ -122,4 +122,15 @@ void dist_allgather3(const void* s0, void* r0, size_t b0, const void* s1, void* 
   check(g_api.GroupEnd(), "ncclGroupEnd");
 }
 
+void dist_allgather4(const void* s0, void* r0, size_t b0, const void* s1, void* r1, size_t b1, const void* s2, void* r2,
+                     size_t b2, const void* s3, void* r3, size_t b3, cudaStream_t st) {
+  nccl_comm_t c = (nccl_comm_t)g_dist.comm;
+  check(g_api.GroupStart(), "ncclGroupStart");
+  check(g_api.AllGather(s0, r0, b0, NCCL_INT8, c, st), "ncclAllGather");
+  check(g_api.AllGather(s1, r1, b1, NCCL_INT8, c, st), "ncclAllGather");
+  check(g_api.AllGather(s2, r2, b2, NCCL_INT8, c, st), "ncclAllGather");
+  check(g_api.AllGather(s3, r3, b3, NCCL_INT8, c, st), "ncclAllGather");
+  check(g_api.GroupEnd(), "ncclGroupEnd");
+}
+
 }  // namespace ries

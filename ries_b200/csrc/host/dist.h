@@ -31,6 +31,8 @@ void dist_finalize();
 /* stream-ordered collectives over raw bytes */
 void dist_allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st);
 /* three all-gathers as one NCCL group (headers, rows, form indices of a sharded pass) */
+void dist_allgather4(const void* s0, void* r0, size_t b0, const void* s1, void* r1, size_t b1, const void* s2, void* r2,
+                     size_t b2, const void* s3, void* r3, size_t b3, cudaStream_t st);
 void dist_allgather3(const void* s0, void* r0, size_t b0, const void* s1, void* r1, size_t b1, const void* s2, void* r2,
                      size_t b2, cudaStream_t st);
 

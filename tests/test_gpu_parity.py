@@ -118,13 +118,17 @@ def test_gpu_node_arena_regrow(product_lib):
                                        {"RIES_STAGE_EVENTS": "1"},
                                        {"RIES_TINY_NODES": "100000", "RIES_TINY_FRONTIER": "48"},
                                        {"RIES_TINY_NODES": "100000", "RIES_TINY_FRONTIER": "100000"},
+                                       {"RIES_FAKE_SHARD": "4", "RIES_SHARD_MIN": "0", "RIES_NO_RANGE_SPLIT": "1"},
+                                       {"RIES_FAKE_SHARD": "3", "RIES_SHARD_MIN": "0", "RIES_RANGE_MIN": "16"},
+                                       {"RIES_FAKE_SHARD": "5", "RIES_SHARD_MIN": "500", "RIES_RANGE_MIN": "1000", "RIES_EVENTS_CAP": "3"},
                                        {"RIES_PERSIST": "1"},
                                        {"RIES_PERSIST": "1", "RIES_NO_TINY": "1", "RIES_NO_GRAPHS": "1"},
                                        {"RIES_PERSIST": "1", "RIES_PERSIST_MAX": "4000000000", "RIES_NO_TINY": "1"}],
                          ids=["general-kernels-only", "mispredicted-small-pass", "no-graphs",
                               "every-pass-sharded-3-virtual-ranks", "large-passes-sharded-2-virtual-ranks-regrow",
                               "passes-fed-in-slices-of-7-forms", "no-tiny-passes", "copy-and-synchronise-per-pass", "no-dependent-launch", "stages-bracketed-by-cuda-events", "mispredicted-tiny-pass",
-                              "every-small-pass-tiny", "one-launch-for-all-positions", "one-launch-no-tiny-no-graphs",
+                              "every-small-pass-tiny", "every-pass-sharded-4-virtual-ranks-second-half-replicated", "every-pass-sharded-3-ranks-split-by-value-range-from-16-rows",
+                              "5-ranks-value-ranges-candidate-buffers-regrow", "one-launch-for-all-positions", "one-launch-no-tiny-no-graphs",
                               "one-launch-for-all-positions-of-every-pass"])
 def test_gpu_pass_variants_agree(product_lib, env_extra):
     """Tiny passes run as three launches (one block enumerates, sorts and matches), small passes through a
