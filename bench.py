@@ -579,7 +579,8 @@ def main():
     }
 
     mode = ("ONE search over %d GPUs: (form, first symbol) pairs dealt round-robin for K1 + hash pre-dedupe, fixed-size "
-            "NCCL all-gather of what survives, replicated sort/merge; every rank prints the full report" % world)
+            "NCCL all-gather of what survives, sort/dedupe/match split by value range, second small exchange, "
+            "replicated merge; every rank prints the full report" % world)
     line = {
         "metric": "expressions_evaluated_per_sec",
         "value": exprs_all / wall_all if wall_all > 0 else 0.0,
