@@ -246,6 +246,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMalloc(&d_ghdr_, RIES_MAX_RANKS * sizeof(SlotHdr)));
     CUDA_CHECK(cudaMalloc(&d_ghdr2_, RIES_MAX_RANKS * sizeof(SlotHdr)));
     CUDA_CHECK(cudaMemset(d_ghdr2_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
+    if (const char* e = getenv("RIES_WATCHDOG_SEC")) watchdog_s_ = atof(e);
     use_range_ = getenv("RIES_NO_RANGE_SPLIT") == 0; /* A/B, test hook: the whole second half replicated */
     if (const char* e = getenv("RIES_RANGE_MIN")) range_min_ = std::max(16u, (u32)strtoul(e, 0, 10)); /* test hook */
     CUDA_CHECK(cudaMemset(d_ghdr_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
@@ -823,8 +824,17 @@ class DeviceEngine : public Engine {
     if (poll_host_) {
       volatile u32* seq = &h_out_->seq;
       const u32 want = pass_seq_;
+      double t_wait0 = 0;
       for (unsigned spins = 1;; spins++) {
         if (*seq == want) break;
+        if ((spins & 0xffffffu) == 0) { /* watchdog: a pass that posts nothing for minutes is a hung kernel, not work */
+          const double now = now_us();
+          if (t_wait0 == 0) t_wait0 = now;
+          else if (now - t_wait0 > watchdog_s_ * 1e6) {
+            fprintf(stderr, "ries_b200: pass %u has not completed after %.0f s (device hung?); giving up\n", want, watchdog_s_);
+            abort();
+          }
+        }
         if ((spins & 0x3ffffu) == 0) { /* every few milliseconds: a driver call takes the lock the launching threads of a batch need */
           const cudaError_t q = cudaStreamQuery(st_);
           if (q == cudaSuccess) {
@@ -1200,6 +1210,7 @@ class DeviceEngine : public Engine {
   SlotHdr* d_ghdr2_ = 0;  /* second exchange of a range-split pass */
   DevBuf<u32> g2_idx_, g2_gap_;
   DevBuf<MatchEvent> g2_events_;
+  double watchdog_s_ = 300.0; /* RIES_WATCHDOG_SEC */
   bool use_range_ = true;
   u32 range_min_ = 65536; /* table rows from which the second half of a sharded pass is split by value range */
   u32 range_new_[2] = {0, 0}, range_ebound_ = 256;

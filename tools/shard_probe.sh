@@ -1,3 +1,4 @@
+# One small search through every sharded-pass variant with virtual ranks (RIES_FAKE_SHARD) on one GPU, compared with the golden text.
 export HOME=/nonexistent
 run() { # name, env..., then args
   name=$1; shift
