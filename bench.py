@@ -554,7 +554,7 @@ def main():
     k1_algo = exprs * K1_BYTES_PER_EXPR
     hbm = {
         "K1_output": hbm_stage("k_expand: 34 B per complete expression it must write", k1_algo, dev_ms[0], dev_launches[0]),
-        "K2_sort": hbm_stage("k_reorder + k_rs_onesweep: 64 B per key", exprs * SORT_BYTES_PER_KEY, dev_ms[1], dev_launches[1]),
+        "K2_sort": hbm_stage("k_keys + k_rs_onesweep: 64 B per key", exprs * SORT_BYTES_PER_KEY, dev_ms[1], dev_launches[1]),
         "K2K3_dedupe_match_merge": hbm_stage("k_classify_compact + k_match_merge_new + k_merge_old: 96 B per merged row",
                                              merge_rows * MERGE_BYTES_PER_ROW, dev_ms[2], dev_launches[2]),
         "peak_kind": peak_kind,

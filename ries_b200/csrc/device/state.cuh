@@ -53,7 +53,7 @@ struct PassArgs {
   u32 cap_nodes, cap_done, cap_events;
   u32 seq; /* number of this pass launch: the last kernel posts it to the host together with the results */
   /* one search over several GPUs: this rank enumerates the forms f with f % shard_world == shard_rank, and
-     the regroup kernels read the all-gathered complete expressions instead of this rank's own */
+     k_keys reads the all-gathered send slots instead of this rank's own expressions */
   int shard_rank, shard_world, gathered;
   int shard_bound; /* rows per rank in the exchange of a sharded pass (send slot, stride of the gathered array) */
   /* sharded pass, second half split by VALUE RANGE (shard.cuh): this rank sorts, dedupes and matches only the
@@ -79,7 +79,7 @@ struct PassCtl {
   u32 nt_before;          /* table rows before this pass */
   u32 n_keys;             /* complete expressions that survive the pre-dedupe and go through the sort */
   u64 dead;               /* dead-ends of the pass */
-  u32 aux_ticket;         /* k_local_filter / k_compact_kept (sharded passes) */
+  u32 aux_ticket;         /* spare ticket */
   u32 n_kept;             /* this rank's complete expressions that survive its local pre-dedupe */
   u64 gen;                /* complete expressions generated (g_ne, ries.c:9190): done_count counts SLOTS, holes included */
   u32 max_nodes, max_done; /* sharded passes: the largest rank's node and expression slots (arena sizing) */
@@ -87,7 +87,7 @@ struct PassCtl {
   u32 bar_gen;             /* k_expand_all: grid-barrier generation (monotonic, survives passes) */
   u64 klo, khi;            /* sharded pass split by value range: this rank keeps the keys in [klo, khi) */
   u32 max_new, max_ev;     /* ... the largest range's new rows and candidates (slot sizes of the next pass) */
-  /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] regroup +
+  /* device clock (%globaltimer, ns) at the start of each stage and at the end of the pass: [0] K1, [1] keys +
      sort, [2] classify/match/merge, [3] refine, [4] end.  Written by thread 0 of block 0 of the stage's first
      kernel (the kernels of a pass run back to back on one stream), read by the host from the copied-back
      block: per-stage device time without a CUDA event per stage on the host's critical path. */

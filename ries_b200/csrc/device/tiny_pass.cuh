@@ -9,7 +9,7 @@
    launches
      k_tiny_front  <<<1, 1024>>>  pass begin; K1 for every expression position (the first EXP_THREADS threads
                                   loop over the positions, a named barrier between them); then regroup +
-                                  sort + classify + match + merge-new of k_small_post by the whole block
+                                  sort + classify + match + merge-new (small_post_body) by the whole block
      k_merge_old   <<<48, ...>>>  unchanged
      k_refine_end  <<<1, 128>>>   refine, then pass end
    Same device functions, same results.  A frontier wider than the prediction allows sets OVF_SMALL and the host

@@ -1121,7 +1121,7 @@ class DeviceEngine : public Engine {
     ch |= uniq_sk_.ensure(done_.cap, st_);
     /* look-back state must start as zeros (stale bits must not look like a live epoch / status) */
     ch |= rs_state_.ensure((done_.cap / RS_CHUNK + 2) * 256, st_, false, true);
-    ch |= cc_state_.ensure(done_.cap / 256 + 2, st_, false, true); /* one word per chunk; the smallest chunk is 256 (k_compact_kept) */
+    ch |= cc_state_.ensure(done_.cap / 256 + 2, st_, false, true); /* one word per chunk of k_classify_compact (2048 keys); sized for chunks of 256 */
     if (ch) ptrs_dirty_ = true;
   }
   void ensure_table(size_t rows) {

@@ -20,7 +20,7 @@ for i, row in enumerate(csv.DictReader(lines)):
     if name not in best or v > best[name][1]:
         best[name] = (int(row["ID"]), v)
 import os
-for name in os.environ.get("KERNELS", "k_expand k_rs_onesweep k_classify_compact k_merge_old k_reorder k_match k_merge_new k_rs_hist_all").split():
+for name in os.environ.get("KERNELS", "k_expand k_keys k_rs_onesweep k_classify_compact k_match_merge_new k_merge_old k_tiny_front").split():
     if name in best:
         print(name, best[name][0])
 PY
