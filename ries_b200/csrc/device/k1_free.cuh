@@ -26,9 +26,11 @@
                  FORM_HOLE), skipped by whoever reads the slot next (~11 % of the slots at -l6).
    Two barriers per round, no look-back, no staging of children, no partial batches but the last. */
 #ifndef XF_THREADS
-#define XF_THREADS 384 /* 2 blocks of 12 warps per SM (the queues of a block take 62 x 416 x 4 B at the default symbol set) */
+#define XF_THREADS 448 /* 2 blocks of 14 warps per SM; measured 256 x 2 or 3: 47.5 ms, 384 x 2: 43.2, 448 x 2: 42.0, 512 x 1: 45.4 */
 #endif
-#define XF_TILE XF_THREADS
+#ifndef XF_TILE
+#define XF_TILE 416 /* prefixes per round: two blocks' queues (62 x (XF_TILE + 32) x 4 B at the default symbol set) fill an SM's shared memory */
+#endif
 #ifndef XF_MIN_BLOCKS
 #define XF_MIN_BLOCKS 2
 #endif
@@ -125,7 +127,7 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
       /* ---- phase P ---- */
       if (have_tile) {
         const u32 p = lvl_begin + tile * XF_TILE + tid;
-        if (p < lvl_end) {
+        if (tid < XF_TILE && p < lvl_end) {
           const Node par = nodes[p];
           if (par.form != FORM_HOLE) {
             const FormDesc& F = forms[par.form];

@@ -196,9 +196,10 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     int occ = 1;
     CUDA_CHECK(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_DYN_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xf_dyn_smem(XF_MAXQ)));
+    const int xf_max_smem = (int)std::min<size_t>(xf_dyn_smem(XF_MAXQ), (size_t)prop.sharedMemPerBlockOptin - 8192);
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, xf_max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_expand, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_CHECK(cudaFuncSetAttribute(k_expand_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xf_dyn_smem(XF_MAXQ)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_expand_all, cudaFuncAttributeMaxDynamicSharedMemorySize, xf_max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_expand_all, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     /* measured (tools/ab_l6.py, -l6 and the default level): no faster than the chained launches -- a small
        position costs its dependent-load chain and two block barriers, not its launch -- so it stays an option */
@@ -212,7 +213,13 @@ class DeviceEngine : public Engine {
     /* tiny passes (tiny_pass.cuh): RIES_NO_TINY switches them off, RIES_TINY_NODES / RIES_TINY_FRONTIER move the
        prediction threshold and the frontier width at which the kernel gives up (test hooks) */
     use_tiny_ = getenv("RIES_NO_TINY") == 0;
-    use_pdl_ = getenv("RIES_NO_PDL") == 0; /* test hook: plain stream order between the K1 launches */
+    /* Programmatic dependent launch between the K1 launches of a pass (the next position's prologue under the
+       previous position's tail) was worth 0.4 ms of 44 at -l6 in round 1 -- and with this round's K1 it DEADLOCKS
+       now and then when a pass overflows an arena and the remaining positions are empty, microsecond-long kernels
+       (tools/hang_repro.sh: 10 of 14 runs of `ries 143 -i -l3` with RIES_ARENA_CAP=4096 hang with it, 0 of 14
+       without; the device is then stuck between the last level's election and the first kernel of the next stage).
+       Off unless asked for. */
+    use_pdl_ = getenv("RIES_PDL") != 0 && getenv("RIES_NO_PDL") == 0;
     if (const char* e = getenv("RIES_TINY_NODES")) tiny_nodes_ = (u32)strtoul(e, 0, 10);
     if (const char* e = getenv("RIES_TINY_FRONTIER")) tiny_frontier_ = (u32)strtoul(e, 0, 10);
     CUDA_CHECK(cudaFuncSetAttribute(k_tiny_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TINY_DYN_SMEM));
@@ -832,6 +839,19 @@ class DeviceEngine : public Engine {
           if (t_wait0 == 0) t_wait0 = now;
           else if (now - t_wait0 > watchdog_s_ * 1e6) {
             fprintf(stderr, "ries_b200: pass %u has not completed after %.0f s (device hung?); giving up\n", want, watchdog_s_);
+            { /* what the device says about it, read on another stream (the engine's is stuck behind the kernel) */
+              cudaStream_t s2;
+              PassCtl c;
+              if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaMemcpyAsync(&c, d_ctl_, sizeof(c), cudaMemcpyDeviceToHost, s2) == cudaSuccess &&
+                  cudaStreamSynchronize(s2) == cudaSuccess)
+                fprintf(stderr, "  control block: lvl [%u, %u) nodes %u done %u ticket %u blocks_done %u keys %u uniq %u events %u overflow %u "
+                                "chunk_ticket %u stamps %llu %llu %llu %llu %llu\n", c.lvl_begin, c.lvl_end, c.node_count, c.done_count,
+                        c.tile_ticket, c.blocks_done, c.n_keys, c.n_uniq, c.n_events, c.overflow, c.chunk_ticket,
+                        (unsigned long long)c.stamp[0], (unsigned long long)(c.stamp[1] ? c.stamp[1] - c.stamp[0] : 0),
+                        (unsigned long long)(c.stamp[2] ? c.stamp[2] - c.stamp[0] : 0), (unsigned long long)(c.stamp[3] ? c.stamp[3] - c.stamp[0] : 0),
+                        (unsigned long long)(c.stamp[4] ? c.stamp[4] - c.stamp[0] : 0));
+            }
             abort();
           }
         }

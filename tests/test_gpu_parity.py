@@ -114,7 +114,7 @@ def test_gpu_node_arena_regrow(product_lib):
                                        {"RIES_FORMS_SLICE": "7"},
                                        {"RIES_NO_TINY": "1"},
                                        {"RIES_NO_HOST_POLL": "1"},
-                                       {"RIES_NO_PDL": "1"},
+                                       {"RIES_PDL": "1"},
                                        {"RIES_STAGE_EVENTS": "1"},
                                        {"RIES_TINY_NODES": "100000", "RIES_TINY_FRONTIER": "48"},
                                        {"RIES_TINY_NODES": "100000", "RIES_TINY_FRONTIER": "100000"},
@@ -126,7 +126,7 @@ def test_gpu_node_arena_regrow(product_lib):
                                        {"RIES_PERSIST": "1", "RIES_PERSIST_MAX": "4000000000", "RIES_NO_TINY": "1"}],
                          ids=["general-kernels-only", "mispredicted-small-pass", "no-graphs",
                               "every-pass-sharded-3-virtual-ranks", "large-passes-sharded-2-virtual-ranks-regrow",
-                              "passes-fed-in-slices-of-7-forms", "no-tiny-passes", "copy-and-synchronise-per-pass", "no-dependent-launch", "stages-bracketed-by-cuda-events", "mispredicted-tiny-pass",
+                              "passes-fed-in-slices-of-7-forms", "no-tiny-passes", "copy-and-synchronise-per-pass", "dependent-launch-between-positions", "stages-bracketed-by-cuda-events", "mispredicted-tiny-pass",
                               "every-small-pass-tiny", "every-pass-sharded-4-virtual-ranks-second-half-replicated", "every-pass-sharded-3-ranks-split-by-value-range-from-16-rows",
                               "5-ranks-value-ranges-candidate-buffers-regrow", "one-launch-for-all-positions", "one-launch-no-tiny-no-graphs",
                               "one-launch-for-all-positions-of-every-pass"])
