@@ -34,6 +34,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
 #include <time.h>
 
 #include <algorithm>
@@ -855,6 +856,8 @@ class DeviceEngine : public Engine {
             abort();
           }
         }
+        /* engines of a batch: more pollers than there may be free cores -- let whoever has work to enqueue run */
+        if (throughput_mode_ && (spins & 0xffu) == 0) sched_yield();
         if ((spins & 0x3ffffu) == 0) { /* every few milliseconds: a driver call takes the lock the launching threads of a batch need */
           const cudaError_t q = cudaStreamQuery(st_);
           if (q == cudaSuccess) {
