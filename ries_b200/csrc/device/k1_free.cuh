@@ -34,6 +34,9 @@
 #ifndef XF_MIN_BLOCKS
 #define XF_MIN_BLOCKS 2
 #endif
+#ifndef XF_MIN_TILE
+#define XF_MIN_TILE 8 /* smallest tile of a position spread over the grid; measured at -l6: fixed 416: K1 42.8 ms, >= 128: 42.2, >= 64: 41.6, >= 32: 40.9, >= 16: 40.3, >= 8: 40.1 */
+#endif
 #define XF_CAP (XF_TILE + 32) /* a queue holds at most 31 left-overs + one tile's pairs of that symbol */
 #define XF_MAXQ (2 * RIES_MAX_SYMS)
 
@@ -112,7 +115,12 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
   }
   const u32 lvl_begin = *(volatile u32*)&ctl->lvl_begin, lvl_end = *(volatile u32*)&ctl->lvl_end;
   const u32 n = lvl_end - lvl_begin;
-  const u32 ntiles = (n + XF_TILE - 1) / XF_TILE;
+  /* A position that cannot fill the grid with full tiles (most of the launches of a search) is spread over all the
+     blocks instead, one smaller tile each: its time is the chain of batches a warp runs one after the other, not
+     the throughput.  Block b then takes tile b -- no ticket -- and its only round drains the queues. */
+  const bool one_round = n < XF_TILE * gridDim.x;
+  const u32 tile_sz = one_round ? min((u32)XF_TILE, max((u32)XF_MIN_TILE, ((n + gridDim.x - 1) / gridDim.x + XF_MIN_TILE - 1u) & ~(XF_MIN_TILE - 1u))) : (u32)XF_TILE;
+  const u32 ntiles = (n + tile_sz - 1) / tile_sz;
   if (PERSIST && ntiles == 0) break; /* uniform over the grid: every block reads the same bounds after the barrier */
   if (ntiles != 0 && !(*(volatile u32*)&ctl->overflow & (OVF_NODES | OVF_DONE))) {
     bool draining = false;
@@ -120,14 +128,14 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
       /* the batch cursor and the queue heads alternate between two copies: there is no barrier at the end of a
          round, so a warp that is done may be here while another still pulls batches of the previous round; the
          copy written here was last read two rounds ago, which every warp has left (it passed the barriers) */
-      if (tid == 0) { s_tile = atomicAdd(&ctl->tile_ticket, 1u); s_next[par2] = 0; }
+      if (tid == 0) { s_tile = one_round ? blockIdx.x : atomicAdd(&ctl->tile_ticket, 1u); s_next[par2] = 0; }
       __syncthreads(); /* also: every warp has left phase C of the previous round (queue entries may be overwritten) */
       const u32 tile = s_tile;
       const bool have_tile = tile < ntiles;
       /* ---- phase P ---- */
       if (have_tile) {
-        const u32 p = lvl_begin + tile * XF_TILE + tid;
-        if (tid < XF_TILE && p < lvl_end) {
+        const u32 p = lvl_begin + tile * tile_sz + tid;
+        if (tid < tile_sz && p < lvl_end) {
           const Node par = nodes[p];
           if (par.form != FORM_HOLE) {
             const FormDesc& F = forms[par.form];
@@ -165,55 +173,41 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
 #ifdef XF_NO_DRAIN_FUSION
       if (tid == 0) s_drain = have_tile ? 0u : 1u;
 #else
-      if (tid == 0) s_drain = (!have_tile || *(volatile u32*)&ctl->tile_ticket >= ntiles) ? 1u : 0u;
+      if (tid == 0) s_drain = (one_round || !have_tile || *(volatile u32*)&ctl->tile_ticket >= ntiles) ? 1u : 0u;
 #endif
       __syncthreads();
       draining = s_drain != 0;
       /* ---- the round's batch list: queue q contributes its full batches (everything when draining) ---- */
       const u32* head = s_head[par2];
       u32 nb_total, nb_live; /* batches of the round; of which from the queues of incomplete prefixes */
-      u32 T_live = 0;        /* slots the round needs in the node arena */
       {
-        /* each lane looks after queues lane, lane + 32, lane + 64 */
-        u32 c[3], run = 0;
+        /* each lane looks after queues lane, lane + 32, lane + 64; exclusive scan in queue order: all of j = 0
+           first, then j = 1, then j = 2 (a group past the last queue is skipped: the branch is uniform) */
+        u32 run = 0;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
+          if ((u32)j * 32 > nq) break;
           const u32 q = (u32)j * 32 + lane;
           const u32 avail = (q < nq) ? s_tail[q] - head[q] : 0;
-          c[j] = draining ? (avail + 31) >> 5 : avail >> 5;
-        }
-        /* exclusive scan in queue order: all of j = 0 first, then j = 1, then j = 2 */
-        u32 tot_live_b = 0, tot_live_s = 0;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          u32 inc = c[j];
+          const u32 c = draining ? (avail + 31) >> 5 : avail >> 5;
+          u32 inc = c;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= (u32)o) inc += v;
           }
-          const u32 q = (u32)j * 32 + lane;
-          if (q <= nq && q < XF_MAXQ + 1) s_cum[q] = run + inc - c[j]; /* every warp writes the same values */
-          /* slots needed in the node arena: entries of the incomplete-prefix queues taken this round */
-          const u32 avail = (q < nq) ? s_tail[q] - head[q] : 0;
-          const u32 take = draining ? avail : (avail & ~31u);
-          u32 tl = (q < nsq) ? take : 0, bl = (q < nsq) ? c[j] : 0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            tl += __shfl_xor_sync(0xffffffffu, tl, o);
-            bl += __shfl_xor_sync(0xffffffffu, bl, o);
-          }
-          tot_live_s += tl; tot_live_b += bl;
+          if (q <= nq) s_cum[q] = run + inc - c; /* every warp writes the same values; q == nq: the sentinel */
           run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        nb_total = run; nb_live = tot_live_b; T_live = tot_live_s;
+        nb_total = run;
         if (lane == 0 && nq >= 96) s_cum[96] = run; /* nq == XF_MAXQ: the sentinel is not any lane's queue */
         __syncwarp();
+        /* the queues of incomplete prefixes come first: their batches are the ones before queue nsq */
+        nb_live = s_cum[nsq];
       }
       /* room for every pair of the round: a live batch b owns node slots [32 b, 32 b + 32) of the round's range,
          a done batch expression slots likewise; only the last batch of a queue can be partial (draining) */
       const u32 slots_live = nb_live * 32u, slots_done = (nb_total - nb_live) * 32u;
-      (void)T_live;
       if (tid == 0) {
         const u32 nbase = slots_live ? atomicAdd(&ctl->node_count, slots_live) : 0;
         const u32 dbase = slots_done ? atomicAdd(&ctl->done_count, slots_done) : 0;

@@ -232,6 +232,79 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
   if (blockIdx.x >= nchunks) return;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = (1u << lane) - 1;
+  if (nchunks == 1) {
+    /* A pass of at most one chunk (most passes of a search are): this block sorts it through all eight digits in
+       the launch of digit 0 -- the keys stay in registers and shared memory from the first load to the last
+       store, there is no ticket, no look-back, no global histogram -- and the other seven launches find nothing
+       to do.  Same ranking as below, so the order inside a bin is again the input order. */
+    if (pass != 0) return;
+    u64* keys_io = Dp->keys[0];
+    u32* idx_io = Dp->idx[0];
+    ASSUME_GLOBAL(keys_io); ASSUME_GLOBAL(idx_io);
+    const u32 wbase_i = warp * (RS_ITEMS * 32) + lane;
+    u64 key[RS_ITEMS];
+    u32 pay[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+      const u32 li = wbase_i + r * 32;
+      key[r] = li < n ? keys_io[li] : 0;
+      pay[r] = li < n ? idx_io[li] : 0;
+    }
+    u32* wh = s_whist[warp];
+#pragma unroll 1
+    for (int shift = 0; shift < 64; shift += 8) {
+      for (u32 j = tid; j < RS_WARPS * 256; j += RS_THREADS) (&s_whist[0][0])[j] = 0;
+      __syncthreads(); /* also: the reload below is over before the exchange buffers are written again */
+      u32 rk[RS_ITEMS];
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; r++) {
+        const bool valid = (wbase_i + r * 32) < n;
+        const u32 d = (u32)(key[r] >> shift) & 255u;
+        const u32 peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | lane));
+        const u32 prev = valid ? wh[d] : 0;
+        __syncwarp();
+        if (valid && (peers & lt) == 0) wh[d] = prev + __popc(peers);
+        __syncwarp();
+        rk[r] = prev + __popc(peers & lt);
+      }
+      __syncthreads();
+      u32 cnt = 0;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; w++) { u32 c = s_whist[w][tid]; s_whist[w][tid] = cnt; cnt += c; }
+      u32 inc = cnt;
+      for (int o = 1; o < 32; o <<= 1) {
+        u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += v;
+      }
+      if (lane == 31) s_wtot[warp] = inc;
+      __syncthreads();
+      {
+        u32 wb = 0;
+        for (u32 w = 0; w < warp; w++) wb += s_wtot[w];
+        s_binex[tid] = wb + inc - cnt;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; r++) {
+        if ((wbase_i + r * 32) < n) {
+          const u32 d = (u32)(key[r] >> shift) & 255u;
+          const u32 lp = s_binex[d] + wh[d] + rk[r];
+          s_keys[lp] = key[r];
+          s_pays[lp] = pay[r];
+        }
+      }
+      __syncthreads();
+      if (shift < 56) {
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+          const u32 li = wbase_i + r * 32;
+          if (li < n) { key[r] = s_keys[li]; pay[r] = s_pays[li]; }
+        }
+      }
+    }
+    for (u32 j = tid; j < n; j += RS_THREADS) { keys_io[j] = s_keys[j]; idx_io[j] = s_pays[j]; }
+    return;
+  }
   const int shift = pass * 8;
   const int src = pass & 1;
   const u64* __restrict__ keys_in = Dp->keys[src];

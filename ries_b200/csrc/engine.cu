@@ -255,6 +255,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMalloc(&d_ghdr2_, RIES_MAX_RANKS * sizeof(SlotHdr)));
     CUDA_CHECK(cudaMemset(d_ghdr2_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
     if (const char* e = getenv("RIES_WATCHDOG_SEC")) watchdog_s_ = atof(e);
+    if (const char* e = getenv("RIES_SMALL_GRID")) small_grid_ = (u32)std::max(1, atoi(e)); /* tuning hook */
     use_range_ = getenv("RIES_NO_RANGE_SPLIT") == 0; /* A/B, test hook: the whole second half replicated */
     if (const char* e = getenv("RIES_RANGE_MIN")) range_min_ = std::max(16u, (u32)strtoul(e, 0, 10)); /* test hook */
     CUDA_CHECK(cudaMemset(d_ghdr_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
@@ -677,7 +678,7 @@ class DeviceEngine : public Engine {
     /* `small`: 0 full grids; 1 a pass predicted to be small; 2, 3 (throughput mode only, see run_pass): mid-size
        passes on a sixteenth / a quarter of the machine */
     const u32 div = small == 2 ? 16u : small == 3 ? 4u : 1u;
-    const u32 g_exp = small == 1 ? 24u : std::max(24u, expand_grid_ / div);
+    const u32 g_exp = small == 1 ? small_grid_ : std::max(24u, expand_grid_ / div);
     const u32 g_wide = small == 1 ? 12u : std::max(24u, wide_grid_ / div);
     const u32 g_keys = small == 1 ? 12u : std::max(16u, (u32)num_sms_ * 4 / div);
     const u32 g_sort = small == 1 ? 12u : std::max(12u, (u32)num_sms_ * RS_MIN_BLOCKS / div);
@@ -1177,6 +1178,7 @@ class DeviceEngine : public Engine {
   int k1_nq_ = 0;
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
   bool use_tiny_ = true, host_prof_ = false, use_pdl_ = true, stage_events_ = false;
+  u32 small_grid_ = 24; /* K1 blocks of a pass predicted to be small */
   double hp_[6] = {0, 0, 0, 0, 0, 0}; /* prepare, enqueue, wait, collect, events, passes */
   static double now_us() {
     struct timespec ts;

@@ -135,6 +135,9 @@ def test_gpu_pass_variants_agree(product_lib, env_extra):
     fused single-block post kernel, the rest through the general kernels, a wrong size prediction is rerun, and K1 can be sharded over (virtual) ranks with the complete expressions
     gathered rank-major: every route must print the same bytes."""
     import subprocess
+    if "RIES_PDL" in env_extra and not os.environ.get("RIES_TEST_PDL"):
+        pytest.skip("experimental route, off in the product (intermittent stall after an arena overflow, DESIGN.md 6); "
+                    "set RIES_TEST_PDL=1 to run it")
     env = dict(os.environ, HOME="/nonexistent", **env_extra)
     exe = os.path.join(ROOT, "ries_b200", "bin", "ries")
     for name in ("t25063_l3_F3_x", "i143_l3", "neg_l2"):
