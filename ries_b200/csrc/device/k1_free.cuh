@@ -96,6 +96,7 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
   const bool track_m = Ap->track_m != 0;
   const double p_min = Ap->p_min;
   const u32 cap_tail = Ap->cap_tail;
+  const bool spread = Ap->k1_spread != 0;
   const u32 shard_world = (u32)Ap->shard_world, shard_rank = (u32)Ap->shard_rank;
   /* queue of (complete, class, slot) = complete * nsq + qoff[class] + slot; symbol of queue q = sym_of_q */
   const u32 qoff1 = (u32)P.cls_n[0], qoff2 = qoff1 + (u32)P.cls_n[1], nsq = qoff2 + (u32)P.cls_n[2];
@@ -118,7 +119,7 @@ __device__ __forceinline__ void expand_body(const DevPtrs* __restrict__ Dp, cons
   /* A position that cannot fill the grid with full tiles (most of the launches of a search) is spread over all the
      blocks instead, one smaller tile each: its time is the chain of batches a warp runs one after the other, not
      the throughput.  Block b then takes tile b -- no ticket -- and its only round drains the queues. */
-  const bool one_round = n < XF_TILE * gridDim.x;
+  const bool one_round = spread && n < XF_TILE * gridDim.x;
   const u32 tile_sz = one_round ? min((u32)XF_TILE, max((u32)XF_MIN_TILE, ((n + gridDim.x - 1) / gridDim.x + XF_MIN_TILE - 1u) & ~(XF_MIN_TILE - 1u))) : (u32)XF_TILE;
   const u32 ntiles = (n + tile_sz - 1) / tile_sz;
   if (PERSIST && ntiles == 0) break; /* uniform over the grid: every block reads the same bounds after the barrier */

@@ -232,6 +232,7 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
   if (blockIdx.x >= nchunks) return;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = (1u << lane) - 1;
+#ifndef RS_NO_SINGLE
   if (nchunks == 1) {
     /* A pass of at most one chunk (most passes of a search are): this block sorts it through all eight digits in
        the launch of digit 0 -- the keys stay in registers and shared memory from the first load to the last
@@ -305,6 +306,7 @@ k_rs_onesweep(const DevPtrs* Dp, const PassCtl* C, const TableState* T, int pass
     for (u32 j = tid; j < n; j += RS_THREADS) { keys_io[j] = s_keys[j]; idx_io[j] = s_pays[j]; }
     return;
   }
+#endif
   const int shift = pass * 8;
   const int src = pass & 1;
   const u64* __restrict__ keys_in = Dp->keys[src];

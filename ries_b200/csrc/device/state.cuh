@@ -58,7 +58,11 @@ struct PassArgs {
   int shard_bound; /* rows per rank in the exchange of a sharded pass (send slot, stride of the gathered array) */
   /* sharded pass, second half split by VALUE RANGE (shard.cuh): this rank sorts, dedupes and matches only the
      gathered rows whose value lies in its range; rows per rank / candidates per rank in the second exchange */
-  int range_split, range_bound, range_ebound, pad_rs;
+  int range_split, range_bound, range_ebound;
+  /* K1: a position that cannot fill the grid with full tiles is spread over all the blocks, one small tile each
+     (k1_free.cuh): the latency of a lone search; off for the engines of a batch, which share the GPU and want
+     full batches instead */
+  int k1_spread;
   /* RHS pass enumerated once for a whole batch of targets (engine.cu, SharedRhs): `der` of an RHS prefix carries
      M = max |value| along the prefix, and what depends on a target's overflow bound is recorded (TailRec) for
      every prefix / child with M >= p_min, the smallest bound in the batch */

@@ -255,6 +255,7 @@ class DeviceEngine : public Engine {
     CUDA_CHECK(cudaMalloc(&d_ghdr2_, RIES_MAX_RANKS * sizeof(SlotHdr)));
     CUDA_CHECK(cudaMemset(d_ghdr2_, 0, RIES_MAX_RANKS * sizeof(SlotHdr)));
     if (const char* e = getenv("RIES_WATCHDOG_SEC")) watchdog_s_ = atof(e);
+    no_spread_ = getenv("RIES_NO_K1_SPREAD") != 0; /* A/B, test hook */
     if (const char* e = getenv("RIES_SMALL_GRID")) small_grid_ = (u32)std::max(1, atoi(e)); /* tuning hook */
     use_range_ = getenv("RIES_NO_RANGE_SPLIT") == 0; /* A/B, test hook: the whole second half replicated */
     if (const char* e = getenv("RIES_RANGE_MIN")) range_min_ = std::max(16u, (u32)strtoul(e, 0, 10)); /* test hook */
@@ -457,7 +458,8 @@ class DeviceEngine : public Engine {
       const bool range = shard && use_range_ && nt_ >= range_min_;
       const u32 rbound = range ? range_bound(side, shard_world) : 0, rebound = range ? range_ebound_ : 0;
       h_args_->range_split = range ? 1 : 0;
-      h_args_->range_bound = (int)rbound; h_args_->range_ebound = (int)rebound; h_args_->pad_rs = 0;
+      h_args_->range_bound = (int)rbound; h_args_->range_ebound = (int)rebound;
+      h_args_->k1_spread = (throughput_mode_ || no_spread_) ? 0 : 1;
       /* tiny: the whole front of the pass in one single-block kernel (tiny_pass.cuh); force_small_post_ is the
          test hook that mispredicts, to exercise the rerun through the general kernels */
       const bool tiny = !shard && !no_tiny && !stage_events_ &&
@@ -1179,6 +1181,7 @@ class DeviceEngine : public Engine {
   bool use_graphs_ = true, use_small_post_ = true, force_small_post_ = false, pass_log_ = false;
   bool use_tiny_ = true, host_prof_ = false, use_pdl_ = true, stage_events_ = false;
   u32 small_grid_ = 24; /* K1 blocks of a pass predicted to be small */
+  bool no_spread_ = false;
   double hp_[6] = {0, 0, 0, 0, 0, 0}; /* prepare, enqueue, wait, collect, events, passes */
   static double now_us() {
     struct timespec ts;

@@ -123,13 +123,14 @@ def test_gpu_node_arena_regrow(product_lib):
                                        {"RIES_FAKE_SHARD": "5", "RIES_SHARD_MIN": "500", "RIES_RANGE_MIN": "1000", "RIES_EVENTS_CAP": "3"},
                                        {"RIES_PERSIST": "1"},
                                        {"RIES_PERSIST": "1", "RIES_NO_TINY": "1", "RIES_NO_GRAPHS": "1"},
-                                       {"RIES_PERSIST": "1", "RIES_PERSIST_MAX": "4000000000", "RIES_NO_TINY": "1"}],
+                                       {"RIES_PERSIST": "1", "RIES_PERSIST_MAX": "4000000000", "RIES_NO_TINY": "1"},
+                                       {"RIES_NO_K1_SPREAD": "1", "RIES_NO_TINY": "1"}],
                          ids=["general-kernels-only", "mispredicted-small-pass", "no-graphs",
                               "every-pass-sharded-3-virtual-ranks", "large-passes-sharded-2-virtual-ranks-regrow",
                               "passes-fed-in-slices-of-7-forms", "no-tiny-passes", "copy-and-synchronise-per-pass", "dependent-launch-between-positions", "stages-bracketed-by-cuda-events", "mispredicted-tiny-pass",
                               "every-small-pass-tiny", "every-pass-sharded-4-virtual-ranks-second-half-replicated", "every-pass-sharded-3-ranks-split-by-value-range-from-16-rows",
                               "5-ranks-value-ranges-candidate-buffers-regrow", "one-launch-for-all-positions", "one-launch-no-tiny-no-graphs",
-                              "one-launch-for-all-positions-of-every-pass"])
+                              "one-launch-for-all-positions-of-every-pass", "full-tiles-only-no-tiny"])
 def test_gpu_pass_variants_agree(product_lib, env_extra):
     """Tiny passes run as three launches (one block enumerates, sorts and matches), small passes through a
     fused single-block post kernel, the rest through the general kernels, a wrong size prediction is rerun, and K1 can be sharded over (virtual) ranks with the complete expressions
