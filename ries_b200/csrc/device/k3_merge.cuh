@@ -314,7 +314,21 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
       hset_insert(hs, hlog, key_of(f.val));
     }
     if (mode == 2) continue;
+    /* the old-table neighbours' side first (one word each): a neighbour of this pass's own side is never tested, so
+       the walk through the gap is not needed for it either -- in a one-sided search that is every gap but the ones
+       next to `x`, where one thread would otherwise walk all the new rows of the gap */
+    u32 oref_prev = 0, oref_next = 0;
     bool test_prev = g > 0, test_next = g < nt;
+    if (test_prev) {
+      oref_prev = tref[g - 1];
+      const bool other_is_lhs = (oref_prev & TREF_LHS) != 0;
+      if (using_x ? other_is_lhs : !other_is_lhs) test_prev = false;
+    }
+    if (test_next) {
+      oref_next = tref[g];
+      const bool other_is_lhs = (oref_next & TREF_LHS) != 0;
+      if (using_x ? other_is_lhs : !other_is_lhs) test_next = false;
+    }
     const bool nb_prev = u > 0 && uniq_gap[u - 1] == g, nb_next = u + 1 < nu && uniq_gap[u + 1] == g;
     if ((test_prev && nb_prev) || (test_next && nb_next)) {
       const SeqKey me = uniq_sk[u];
@@ -329,10 +343,7 @@ __global__ void k_match_merge_new(const DevPtrs* Dp, const PassArgs* A, PassCtl*
     }
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !test_prev : !test_next) continue;
-      const u32 oref = tref[side == 0 ? g - 1 : g];
-      const bool other_is_lhs = (oref & TREF_LHS) != 0;
-      if (using_x ? other_is_lhs : !other_is_lhs) continue;
-      const Row o = heap[oref & ~TREF_LHS];
+      const Row o = heap[(side == 0 ? oref_prev : oref_next) & ~TREF_LHS];
       const Row& L = using_x ? f : o;
       const Row& R = using_x ? o : f;
       double total = L.der - R.der;
