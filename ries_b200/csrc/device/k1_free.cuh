@@ -24,6 +24,10 @@
                    per output array while the first batches are already running.
                  The last round of a block drains what is left.  A pair that fails leaves a HOLE (form =
                  FORM_HOLE), skipped by whoever reads the slot next (~11 % of the slots at -l6).
+     SPREAD      a position with fewer prefixes than blocks x XF_TILE (four launches in five) would leave most
+                 blocks idle while a few run ~8 batches per warp one after the other: it is cut into one small
+                 tile per block instead (block b = tile b, no ticket), whose single round drains the queues.
+                 PassArgs::k1_spread; off for the engines of a batch, which share the GPU and want full batches.
    Two barriers per round, no look-back, no staging of children, no partial batches but the last. */
 #ifndef XF_THREADS
 #define XF_THREADS 448 /* 2 blocks of 14 warps per SM; measured 256 x 2 or 3: 47.5 ms, 384 x 2: 43.2, 448 x 2: 42.0, 512 x 1: 45.4 */
